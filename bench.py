@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""PRMF hot-path benchmark (contract: see the task statement / DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One *step* = one outer iteration of `nmf_pathway` (reference script/prmf_runner.py:715-774) on the
+recount2-shape synthetic instance (BASELINE.json configs[1]: 37 032 samples x 6 750 genes, k = 10,
+300 KEGG-size random pathways): k multinomial draws of the active pathways, `modulus` = 10 inner
+multiplicative updates with their objectives, and one `restrict` over the full candidate table.
+`value` is outer iterations per second with X resident in HBM; `e2e` is the same step driven with
+host buffers (X, U, V uploaded from pinned memory and U, V, objective read back every step).
+With N > 1 the rows of X and U are sharded over the ranks (strong scaling; one NCCL all-reduce of
+[X^T U | U^T U] per inner step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M, N_GENES, K, P = 37032, 6750, 10, 300
+MODULUS = 10
+METRIC = "prmf_outer_iterations_per_sec"
+UNIT = "outer_it/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--m", type=int, default=M)
+    ap.add_argument("--n", type=int, default=N_GENES)
+    ap.add_argument("--k", type=int, default=K)
+    ap.add_argument("--pathways", type=int, default=P)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-inner-steps", type=int, default=2)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "recount2-shape synthetic %dx%d fp64, k=%d, %d random KEGG-size pathways" % (a.m, a.n, a.k, a.pathways)
+
+
+def make_pathways(a):
+    from prmf_b200 import pack_pathways, synth
+    rng = np.random.Generator(np.random.PCG64(0))
+    Gs = synth.random_pathway_graphs(rng, a.n, a.pathways)
+    nodelist = list(range(a.n))
+    return Gs, nodelist, pack_pathways(Gs, nodelist)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks (nvidia-smi sampled during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=float(max(power)))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (a port of the reference's numpy/scipy path) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_outer_iteration_rate(X, Gs, nodelist, k, n_inner, seed=1):
+    """Time `n_inner` inner steps (update + objective, prmf_runner.py:419-449) and one `restrict`
+    (:129-194) of the CPU oracle at the full shape and extrapolate to one outer iteration
+    (10 inner steps + restrict).  Returns (outer_it_per_s, detail dict)."""
+    from oracle import prmf_oracle as O
+    rng = np.random.Generator(np.random.PCG64(seed))
+    m, n = X.shape
+    U = 3 * (1 - rng.random((m, k))); V = 3 * (1 - rng.random((n, k)))
+    t0 = time.perf_counter()
+    tables = O.PathwayTables(Gs, nodelist)
+    t_tables = time.perf_counter() - t0
+    normX = np.linalg.norm(X)
+    gamma, delta = normX / k, 10 / normX
+    active = list(range(k))
+    t0 = time.perf_counter()
+    for _ in range(n_inner):
+        U, V = O.update_step(X, U, V, tables, active, gamma, delta)
+        O.objective(X, U, V, tables, active, gamma, delta)
+    t_inner = (time.perf_counter() - t0) / n_inner
+    cands = {kk: [(p, 1) for p in range(len(tables))] for kk in range(k)}
+    t0 = time.perf_counter()
+    O.restrict(V, tables, cands)
+    t_restrict = time.perf_counter() - t0
+    t_outer = MODULUS * t_inner + t_restrict
+    return 1.0 / t_outer, {"s_per_inner_step": t_inner, "s_restrict": t_restrict, "s_tables": t_tables}
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
+        if n:
+            return int(max(n))
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
+def run_reference_arm(a):
+    """`--impl reference`: the reference's CPU implementation of the path (the oracle port; the Python
+    reference itself needs networkx<2 and cannot run on the GPU box) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from prmf_b200 import synth  # noqa: F401  (instance generators are shared)
+    rng = np.random.Generator(np.random.PCG64(1234))
+    X = rng.random((a.m, a.n))
+    Gs, nodelist, _ = make_pathways(a)
+    rates = []
+    total = a.warmup + a.steps
+    # each step = a bounded sample: `cpu_inner_steps` inner steps + 1 restrict, extrapolated to 10 + 1
+    for s in range(total):
+        r, detail = cpu_outer_iteration_rate(X, Gs, nodelist, a.k, a.cpu_inner_steps, seed=s)
+        if s >= a.warmup:
+            rates.append(r)
+        if time.perf_counter() - T_START > 240 and rates:
+            break
+    value = float(np.mean(rates))
+    cores = host_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": len(rates), "warmup": a.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "step": "1 outer iteration = 10 inner steps + restrict"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d inner steps + 1 restrict at full shape per step, extrapolated to 10 + 1" % a.cpu_inner_steps},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    from prmf_b200 import CudaEngine
+    from prmf_b200.dist import DistContext, row_block
+    from prmf_b200.engine import nccl_load, nccl_unique_id
+    from prmf_b200.solver import init_latent_to_pathway_data, restrict_from_tables, sample_active
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    ctx = DistContext.from_env()
+    if ctx.world != a.gpus:
+        raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (a.gpus, ctx.world))
+    dev = ctx.local_rank if ctx.world > 1 else 0
+    torch.cuda.set_device(dev)
+    stream = torch.cuda.Stream(device=dev)
+    lo, hi = row_block(a.m, ctx.world, ctx.rank)
+    m_local = hi - lo
+    Gs, nodelist, packed = make_pathways(a)
+
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1234 + ctx.rank)
+    Xd = torch.rand((m_local, a.n), dtype=torch.float64, device="cuda", generator=gen)
+    eng = CudaEngine(m_local, a.m, a.n, a.k, device=dev, stream=stream.cuda_stream)
+    if ctx.world > 1:
+        nccl_load()
+        uid = ctx.broadcast_bytes(nccl_unique_id() if ctx.rank == 0 else None)
+        eng.attach_comm(ctx.rank, ctx.world, uid)
+    eng.set_X(Xd)
+    eng.set_pathways(packed)
+    normX = float(np.sqrt(eng.normX_sq))
+    gamma, delta = normX / a.k, 10 / normX
+
+    np.random.seed(1)
+    U0 = 3 * (1 - np.random.rand(a.m, a.k))[lo:hi]
+    V0 = 3 * (1 - np.random.rand(a.n, a.k))
+    eng.set_UV(U0, V0)
+    full_cands = init_latent_to_pathway_data(a.k, packed.P)
+
+    def outer_iteration():
+        active = sample_active(full_cands, a.k)
+        eng.set_active(active)
+        parts, _, _ = eng.step(MODULUS, gamma, delta)
+        mass, qn, _ = eng.scores()
+        restrict_from_tables(mass, qn, full_cands)
+        return parts
+
+    def sync_all():
+        if ctx.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        outer_iteration()
+    eng.kernel_times(reset=True)
+    launches0 = eng.launch_count
+    sampler = ClockSampler(dev)
+    sync_all()
+    sampler.start()
+    eng.set_profiling(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(a.steps):
+        parts = outer_iteration()
+    e1.record(stream)
+    sync_all()
+    eng.set_profiling(False)
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count - launches0
+    kt = eng.kernel_times(reset=True)
+    if ctx.world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / a.steps
+    value = 1000.0 / ms_per_step
+
+    # roofline of the X-stream kernels (algorithmic bytes per launch / mean launch duration)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    bytes_xv = m_local * a.n * 8 + a.n * a.k * 8 + m_local * a.k * 8
+    bytes_xtu = m_local * a.n * 8 + m_local * a.k * 8 + a.n * a.k * 8
+    xv_ms = kt["xv_ms"] / max(1, kt["xv_launches"])
+    xtu_ms = kt["xtu_ms"] / max(1, kt["xtu_launches"])
+    ach_xv = bytes_xv / (xv_ms * 1e-3) / 1e9 if xv_ms > 0 else 0.0
+    ach_xtu = bytes_xtu / (xtu_ms * 1e-3) / 1e9 if xtu_ms > 0 else 0.0
+    step_bytes = bytes_xv + bytes_xtu
+    inner_ms = ms_per_step / MODULUS
+    dominant = "xtu_kernel (X^T.U)" if xtu_ms >= xv_ms else "xv_kernel (X.V)"
+    ach = ach_xtu if xtu_ms >= xv_ms else ach_xv
+    roofline = {
+        "bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+        "traffic": None, "peak_source": peak_src,
+        "xv": {"ms": xv_ms, "GBps": ach_xv, "frac": ach_xv / peak, "bytes": bytes_xv},
+        "xtu": {"ms": xtu_ms, "GBps": ach_xtu, "frac": ach_xtu / peak, "bytes": bytes_xtu},
+        "inner_step": {"ms": inner_ms, "bytes": step_bytes, "GBps": step_bytes / (inner_ms * 1e-3) / 1e9,
+                       "frac": step_bytes / (inner_ms * 1e-3) / 1e9 / peak,
+                       "x_stream_share_of_step": (xv_ms + xtu_ms) / inner_ms if inner_ms > 0 else None},
+    }
+
+    # e2e: the same outer iteration with HOST buffers (pinned X, U, V in; U, V, objective out)
+    e2e = None
+    if not a.no_e2e:
+        Xh = torch.empty((m_local, a.n), dtype=torch.float64, pin_memory=True)
+        Xh.copy_(Xd)
+        del Xd
+        Uh = torch.empty((m_local, a.k), dtype=torch.float64, pin_memory=True)
+        Vh = torch.empty((a.n, a.k), dtype=torch.float64, pin_memory=True)
+        Uh.copy_(torch.from_numpy(np.ascontiguousarray(U0))); Vh.copy_(torch.from_numpy(V0))
+        Xn, Un, Vn = Xh.numpy(), Uh.numpy(), Vh.numpy()
+
+        def e2e_iteration():
+            eng.set_X(Xn)                       # H2D of this step's input
+            eng.set_UV(Un, Vn)
+            active = sample_active(full_cands, a.k)
+            eng.set_active(active)
+            p, _, _ = eng.step(MODULUS, gamma, delta)
+            mass, qn, _ = eng.scores()
+            restrict_from_tables(mass, qn, full_cands)
+            Uo, Vo = eng.get_UV()               # D2H of the result
+            return float(p[-1, 4]), Uo, Vo
+
+        n_e2e = max(2, min(a.steps, 5))
+        e2e_iteration()
+        sync_all()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(n_e2e):
+            e2e_iteration()
+        e1.record(stream)
+        sync_all()
+        wall_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+        ems = max(e0.elapsed_time(e1) / n_e2e, wall_ms)
+        if ctx.world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ems], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        e2e = {"value": 1000.0 / ems, "unit": UNIT, "ms_per_step": ems,
+               "h2d_bytes_per_step": int(m_local * a.n * 8 + (m_local + a.n) * a.k * 8),
+               "d2h_bytes_per_step": int((m_local + a.n) * a.k * 8 + MODULUS * 64 + 2 * a.k * packed.P * 8),
+               "steps": n_e2e}
+        Xcpu = Xn
+    else:
+        Xcpu = None
+
+    cpu = None
+    if ctx.rank == 0 and ctx.world == 1 and not a.no_cpu_baseline and Xcpu is not None:
+        rate, detail = cpu_outer_iteration_rate(np.asarray(Xcpu), Gs, nodelist, a.k, a.cpu_inner_steps)
+        cpu = {"value": rate, "unit": UNIT, "cores": host_threads(), "kind": "port",
+               "sample": "%d inner steps + 1 restrict of the numpy/scipy oracle at full shape, extrapolated to 10 + 1"
+                         % a.cpu_inner_steps, **detail}
+
+    eng.close()
+    if ctx.rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "step": "1 outer iteration = 10 inner steps + scores/restrict",
+                       "parallelism": "rows of X,U sharded over %d GPU(s)" % a.gpus,
+                       "l2": "inputs larger than L2 (X block %.2f GB per GPU per pass)" % (m_local * a.n * 8 / 1e9),
+                       "inner_steps_per_s": 1000.0 / inner_ms},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "final_obj": float(parts[-1, 4]),
+        }
+        print(json.dumps(line))
+    if ctx.world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+T_START = time.perf_counter()
+
+if __name__ == "__main__":
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)

@@ -1,0 +1,137 @@
+/* prmf_b200.h -- C ABI of the B200-native PRMF hot path (libprmf_b200.so).
+ *
+ * The reference (gitter-lab/prmf) is pure Python and has no FFI; the boundary this library replaces is
+ * the numeric body of `script/prmf_runner.py`:
+ *     nmf_pathway                     :556-792   (driver; stays on the host, calls the entry points below)
+ *     nmf_manifold_vec_update         :374-451   -> prmf_step
+ *     nmf_manifold_vec_update_tradeoff:497-554   -> prmf_step (tradeoff >= 0)
+ *     nmf_manifold_vec_obj            :336-372   -> prmf_step (objective parts per inner step)
+ *     normalize_laplacian             :56-65     -> prmf_set_pathways (derived once, on the device)
+ *     score_latent_pathway_match_global :115-127 , restrict :129-194 (scores)   -> prmf_scores
+ *     force_distinct_lapls            :209-258   (edge weights)                 -> prmf_scores
+ *     find_mins                       :37-54                                    -> prmf_scores (quad_raw)
+ *
+ * Conventions: every call returns 0 on success and a negative code on failure (the text is available
+ * from prmf_last_error); plain pointers and sizes only; the caller owns every host pointer for the
+ * duration of the call; the library owns all device memory until prmf_destroy.  A handle is bound to
+ * one GPU and one host thread.  Matrices are C-order (row-major) IEEE fp64.  There is no CPU fallback:
+ * without a CUDA device prmf_create fails.
+ */
+#ifndef PRMF_B200_H
+#define PRMF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct prmf_handle prmf_handle;
+
+#define PRMF_OK              0
+#define PRMF_ERR_ARG        -1
+#define PRMF_ERR_CUDA       -2
+#define PRMF_ERR_STATE      -3
+#define PRMF_ERR_NCCL       -4
+#define PRMF_ERR_NOMEM      -5
+
+#define PRMF_OBJ_STRIDE      8   /* doubles per inner step written by prmf_step (see below) */
+#define PRMF_UNIQUE_ID_BYTES 128
+
+/* ABI version of this header (bumped on any signature change). */
+int prmf_abi_version(void);
+
+/* Create a solver handle on GPU `device` for a row block of `m_local` samples (of `m_global` in the
+ * whole job), `n` genes and `k` latent factors.  `stream` is a cudaStream_t to run on (e.g. torch's
+ * current stream) or NULL for a private stream.  Replaces the array allocations of
+ * nmf_pathway (prmf_runner.py:647-655). */
+int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global, int64_t n, int k,
+                void* stream);
+int prmf_destroy(prmf_handle* h);
+
+/* Last error text of `h` (or of the last failed prmf_create when h is NULL). */
+const char* prmf_last_error(const prmf_handle* h);
+
+/* Upload this rank's row block of X (host pointer, `ld` doubles between rows) and compute the local
+ * sum of squares.  prmf_set_X_device takes a DEVICE pointer instead (copied into the library's padded
+ * layout on the handle's stream).  X argument of nmf_pathway / nmf_manifold_vec_update (:556,:374). */
+int prmf_set_X(prmf_handle* h, const double* X_host, int64_t ld);
+int prmf_set_X_device(prmf_handle* h, const double* X_dev, int64_t ld);
+
+/* Global ||X||_F^2 (all-reduced when a communicator is attached); `np.linalg.norm(X)` at :640. */
+int prmf_get_normX_sq(prmf_handle* h, double* out);
+
+/* All P pathways packed block-diagonally over LOCAL support indices (replaces the per-pathway n x n
+ * scipy W, D, L matrices and support lists built at prmf_runner.py:673-696):
+ *   path_ptr[P+1]     offsets into support_idx / rows              (path_ptr[P] = S)
+ *   support_idx[S]    gene index (0..n-1) of every support node, pathway after pathway
+ *   row_ptr[S+1]      offsets into col_local / w                   (row_ptr[S] = E)
+ *   col_local[E]      neighbour as an index INTO THE SAME PATHWAY's support (0..s_p-1)
+ *   w[E]              symmetric edge weights (each undirected edge appears in both rows; a self loop once)
+ * The library derives degrees, diag(L) and diag(L)^-1/2 (normalize_laplacian, :56-65). */
+int prmf_set_pathways(prmf_handle* h, int32_t P, const int64_t* path_ptr, const int32_t* support_idx,
+                      const int64_t* row_ptr, const int32_t* col_local, const double* w);
+
+/* Initial / current factors.  U is this rank's m_local x k block, V is n x k (replicated).  Either
+ * pointer may be NULL to skip it.  U_init / V_init of nmf_pathway (:650-655) and its return value. */
+int prmf_set_UV(prmf_handle* h, const double* U_local, const double* V);
+int prmf_get_UV(prmf_handle* h, double* U_local, double* V);
+
+/* Active pathway of every factor for the following inner steps: k_to_lapl_ind of :717-730 /
+ * map_k_to_lapls :260-270. */
+int prmf_set_active(prmf_handle* h, const int32_t* pathway_of_factor);
+
+/* `n_steps` inner multiplicative updates (nmf_manifold_vec_update, :419-449) with the objective of
+ * every step (nmf_manifold_vec_obj, :336-372).  tradeoff < 0 keeps gamma/delta fixed; tradeoff in [0,1]
+ * feeds gamma = delta = (1-t)*recon/(t*manifold) back after every step on the device (:542-548).
+ * obj_parts (host, n_steps x PRMF_OBJ_STRIDE): recon, manifold, ignore, fro, obj, gamma, delta, recon^2
+ * (gamma/delta are the values the step was computed with).  gamma_delta_out (host, 2 doubles or NULL):
+ * gamma, delta to use for the next step.  All steps are enqueued without host synchronisation; the
+ * call returns after one synchronisation at the end.  With a communicator attached every step includes
+ * the all-reduce of X^T U, U^T U and sum(U^2) over ranks. */
+int prmf_step(prmf_handle* h, int n_steps, double gamma, double delta, double tradeoff,
+              double* obj_parts, double* gamma_delta_out);
+
+/* Enqueue-only variant for timing: no synchronisation, results stay on the device until
+ * prmf_step_collect copies the last `n_steps` rows. */
+int prmf_step_async(prmf_handle* h, int n_steps, double gamma, double delta, double tradeoff);
+int prmf_step_collect(prmf_handle* h, int n_steps, double* obj_parts, double* gamma_delta_out);
+
+/* Factor x pathway tables from the current V (each k x P, row-major, host pointers, any may be NULL):
+ *   mass[k][p]      = sum_{i in supp_p} vhat_i^2          (score_mass^2, :123; vhat = v_k/||v_k||)
+ *   quad_norm[k][p] = vhat^T Lhat_p vhat                  (1 - score_manifold, :124; objective :350)
+ *   quad_raw[k][p]  = v_k^T L_p v_k                       (force_distinct_lapls :232; find_mins :49) */
+int prmf_scores(prmf_handle* h, double* mass, double* quad_norm, double* quad_raw);
+
+/* Best-iterate bookkeeping of nmf_pathway (:745-750, :778-782) without host traffic. */
+int prmf_snapshot_best(prmf_handle* h);
+int prmf_restore_best(prmf_handle* h);
+
+/* Exact residual ||X - U V^T||_F^2 by one extra pass over X (verification of the pass-free identity
+ * used inside prmf_step; all-reduced when a communicator is attached). */
+int prmf_residual_sq(prmf_handle* h, double* out);
+
+/* ---- multi-GPU (one handle per rank / process) ------------------------------------------------------
+ * prmf_nccl_load dlopens the NCCL the host process already uses (path of libnccl.so.2, or NULL to look
+ * it up); rank 0 calls prmf_comm_unique_id and ships the 128 bytes to the other ranks (any transport,
+ * e.g. torch.distributed.broadcast); every rank calls prmf_comm_init.  Afterwards prmf_set_X reduces
+ * ||X||^2 and prmf_step all-reduces the packed [X^T U | U^T U | sum U^2] buffer every inner step. */
+int prmf_nccl_load(const char* libnccl_path);
+int prmf_comm_unique_id(uint8_t* id_out /* PRMF_UNIQUE_ID_BYTES */);
+int prmf_comm_init(prmf_handle* h, int rank, int nranks, const uint8_t* id);
+
+/* ---- introspection used by bench.py and the tests ---------------------------------------------------*/
+/* Number of kernel launches issued by this handle so far. */
+int64_t prmf_launch_count(const prmf_handle* h);
+/* Device time (ms, CUDA events on the handle's stream) of the X.V pass and the X^T.U pass accumulated
+ * since the last call with reset != 0; `launches` receives the number of timed launches of each. */
+int prmf_kernel_times(prmf_handle* h, int reset, double* xv_ms, double* xtu_ms, int64_t* launches);
+/* Enable (1) / disable (0) per-kernel event timing inside prmf_step (off by default). */
+int prmf_set_profiling(prmf_handle* h, int on);
+/* The cudaStream_t the handle launches on. */
+void* prmf_stream(const prmf_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRMF_B200_H */

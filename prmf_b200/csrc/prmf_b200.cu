@@ -1,0 +1,766 @@
+// libprmf_b200.so -- C ABI (include/prmf_b200.h) over the sm_100a kernels in kernels.cuh.
+// Host orchestration of one PRMF inner step (reference prmf_runner.py:419-449):
+//
+//   xv_kernel           A  = X.V                       pass 1 over X          (:420)
+//   u_update_kernel     U <- U*A/(U.Gv+U), Gu partials                        (:421-422,:425)
+//   xtu_kernel          B partials = X^T.U_new         pass 2 over X          (:424)
+//   reduce_pack_kernel  red = [B | Gu | .]  (fixed-order sums)
+//   ncclAllReduce(red)                                 only with a communicator
+//   fro_from_gram       red[..] = trace(Gu) = sum(U^2)                        (:359)
+//   v_update_kernel     V_new (factor-major copy), Gv/VB partials             (:425-444)
+//   vt_to_v_kernel      gene-major V refreshed
+//   objective_kernel    Gv_new, recon/manifold/ignore/fro/obj, tradeoff       (:336-372,:542-548)
+#include "../../include/prmf_b200.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "nccl_dyn.h"
+
+using namespace prmf;
+
+namespace {
+
+thread_local std::string g_create_error;
+NcclApi g_nccl;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct prmf_handle {
+    int device = 0;
+    int sm_count = 148;
+    int64_t m = 0, m_global = 0, n = 0;
+    int k = 0;
+    int64_t ldx = 0, ldvt = 0;
+    int n2 = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+
+    // device buffers
+    double* X = nullptr;
+    bool own_X = true;
+    double *U = nullptr, *V = nullptr, *Vt = nullptr, *Ub = nullptr, *Vb = nullptr, *Gvb = nullptr;
+    double* A = nullptr;
+    double *Gv = nullptr, *Gu_part = nullptr, *Gv_part = nullptr, *VB_part = nullptr;
+    double* Bpart = nullptr;
+    double* red = nullptr;
+    double *normX_sq = nullptr, *scal_part = nullptr;
+    double* gd = nullptr;
+    double* obj = nullptr;
+    int* step_counter = nullptr;
+    int obj_capacity = 0;
+    int32_t *active = nullptr, *pos = nullptr;
+    bool have_X = false, have_UV = false, have_pw = false, have_active = false, pos_dirty = true;
+    std::vector<int32_t> active_host;
+
+    // pathways
+    Pathways pw{};
+    int64_t S = 0, E = 0;
+    std::vector<void*> pw_allocs;
+    std::vector<int64_t> path_ptr_host;
+    std::vector<int32_t> support_host;
+
+    // launch geometry
+    int xv_grid = 0, uu_grid = 0, uu_rows = 0, vu_grid = 0, vu_rows = 0;
+    int panels = 0, panel_w = 0, chunks = 0;
+    int64_t rows_per_chunk = 0;
+    int ktile = 0, nq = 1;
+
+    // multi-GPU
+    NcclComm comm = nullptr;
+    int rank = 0, nranks = 1;
+
+    // introspection
+    int64_t launches = 0;
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<std::pair<int, int>> ev_pairs;   // (kind, pool index of start); kind 0 = xv, 1 = xtu
+    double xv_ms = 0, xtu_ms = 0;
+    int64_t xv_n = 0, xtu_n = 0;
+};
+
+namespace {
+
+int fail(prmf_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(h, PRMF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+#define LAUNCH_CHECK(name)                                                                    \
+    do {                                                                                      \
+        h->launches++;                                                                        \
+        cudaError_t e_ = cudaGetLastError();                                                  \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(h, PRMF_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
+    } while (0)
+
+template <typename T>
+int dalloc(prmf_handle* h, T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    if (e != cudaSuccess)
+        return fail(h, PRMF_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    return PRMF_OK;
+}
+
+int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+int pick_ktile(int k) {
+    if (k <= 10) return k;
+    int tiles = (k + 9) / 10;
+    return (k + tiles - 1) / tiles;
+}
+
+int pick_nq(int k) {
+    int pairs = k * k;
+    int q = (pairs + 255) / 256;
+    if (q <= 1) return 1;
+    if (q <= 4) return 4;
+    if (q <= 16) return 16;
+    return 64;
+}
+
+template <typename F>
+int set_smem(prmf_handle* h, F kernel, size_t bytes) {
+    if (bytes > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return PRMF_OK;
+}
+
+// ---- templated launch dispatch ---------------------------------------------------------------------
+constexpr int kRW = 4;
+
+template <int KT>
+void launch_xv_t(prmf_handle* h, int k0) {
+    xv_kernel<KT, kRW><<<h->xv_grid, 256, 0, h->stream>>>(h->X, h->ldx, h->m, h->n2, h->Vt, h->ldvt, k0, h->k, h->A);
+}
+template <int KT>
+void launch_xtu_t(prmf_handle* h, int k0) {
+    dim3 grid(h->panels, h->chunks);
+    xtu_kernel<KT><<<grid, 256, 0, h->stream>>>(h->X, h->ldx, h->m, (int)h->n, h->U, h->k, k0, h->panel_w,
+                                                h->rows_per_chunk, h->Bpart);
+}
+
+#define KT_SWITCH(kt, FN, ...)          \
+    switch (kt) {                       \
+        case 1: FN<1>(__VA_ARGS__); break;   \
+        case 2: FN<2>(__VA_ARGS__); break;   \
+        case 3: FN<3>(__VA_ARGS__); break;   \
+        case 4: FN<4>(__VA_ARGS__); break;   \
+        case 5: FN<5>(__VA_ARGS__); break;   \
+        case 6: FN<6>(__VA_ARGS__); break;   \
+        case 7: FN<7>(__VA_ARGS__); break;   \
+        case 8: FN<8>(__VA_ARGS__); break;   \
+        case 9: FN<9>(__VA_ARGS__); break;   \
+        default: FN<10>(__VA_ARGS__); break; \
+    }
+
+int launch_xv(prmf_handle* h) {
+    if (h->m == 0) return PRMF_OK;
+    for (int k0 = 0; k0 < h->k; k0 += h->ktile) {
+        int kt = std::min(h->ktile, h->k - k0);
+        KT_SWITCH(kt, launch_xv_t, h, k0);
+        LAUNCH_CHECK("xv_kernel");
+    }
+    return PRMF_OK;
+}
+
+int launch_xtu(prmf_handle* h) {
+    if (h->m == 0) {
+        CU(cudaMemsetAsync(h->Bpart, 0, sizeof(double) * h->chunks * h->n * h->k, h->stream));
+        return PRMF_OK;
+    }
+    for (int k0 = 0; k0 < h->k; k0 += h->ktile) {
+        int kt = std::min(h->ktile, h->k - k0);
+        KT_SWITCH(kt, launch_xtu_t, h, k0);
+        LAUNCH_CHECK("xtu_kernel");
+    }
+    return PRMF_OK;
+}
+
+#define NQ_SWITCH(nq, EXPR)                    \
+    switch (nq) {                              \
+        case 1: { constexpr int NQ = 1; EXPR; } break;   \
+        case 4: { constexpr int NQ = 4; EXPR; } break;   \
+        case 16: { constexpr int NQ = 16; EXPR; } break; \
+        default: { constexpr int NQ = 64; EXPR; } break; \
+    }
+
+size_t uu_smem(const prmf_handle* h) { return sizeof(double) * ((size_t)h->k * h->k + (size_t)h->uu_rows * h->k); }
+size_t vu_smem(const prmf_handle* h) { return sizeof(double) * ((size_t)h->k * h->k + (size_t)h->vu_rows * h->k); }
+size_t gram_smem(const prmf_handle* h) { return sizeof(double) * ((size_t)h->vu_rows * h->k); }
+size_t obj_smem(const prmf_handle* h) { return sizeof(double) * ((size_t)h->k * h->k); }
+
+int launch_u_update(prmf_handle* h) {
+    NQ_SWITCH(h->nq, (u_update_kernel<NQ><<<h->uu_grid, 256, uu_smem(h), h->stream>>>(
+                         h->U, h->A, h->Gv, h->m, h->k, h->uu_rows, h->Gu_part)));
+    LAUNCH_CHECK("u_update_kernel");
+    return PRMF_OK;
+}
+
+int launch_v_update(prmf_handle* h) {
+    NQ_SWITCH(h->nq, (v_update_kernel<NQ><<<h->vu_grid, 256, vu_smem(h), h->stream>>>(
+                         h->V, h->Vt, h->ldvt, h->red, (int)h->n, h->k, h->pw, h->active, h->pos, h->gd,
+                         h->vu_rows, h->Gv_part, h->VB_part)));
+    LAUNCH_CHECK("v_update_kernel");
+    const int64_t nk = h->n * h->k;
+    vt_to_v_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, h->stream>>>(h->Vt, h->ldvt, (int)h->n, h->k, h->V);
+    LAUNCH_CHECK("vt_to_v_kernel");
+    return PRMF_OK;
+}
+
+// Gv = V^T V from scratch (after set_UV / restore)
+int recompute_Gv(prmf_handle* h) {
+    NQ_SWITCH(h->nq, (gram_rows_kernel<NQ><<<h->vu_grid, 256, gram_smem(h), h->stream>>>(
+                         h->V, h->n, h->k, h->vu_rows, h->Gv_part)));
+    LAUNCH_CHECK("gram_rows_kernel");
+    const int kk2 = h->k * h->k;
+    sum_gram_parts_kernel<<<(kk2 + 255) / 256, 256, 0, h->stream>>>(h->Gv_part, h->vu_grid, kk2, h->Gv);
+    LAUNCH_CHECK("sum_gram_parts_kernel");
+    return PRMF_OK;
+}
+
+int ensure_pos(prmf_handle* h) {
+    if (!h->pos_dirty) return PRMF_OK;
+    CU(cudaMemsetAsync(h->pos, 0xff, sizeof(int32_t) * h->n * h->k, h->stream));
+    dim3 grid(4, h->k);
+    build_pos_kernel<<<grid, 128, 0, h->stream>>>(h->pw, h->active, h->k, h->pos);
+    LAUNCH_CHECK("build_pos_kernel");
+    h->pos_dirty = false;
+    return PRMF_OK;
+}
+
+int allreduce(prmf_handle* h, double* buf, size_t count) {
+    if (!h->comm) return PRMF_OK;
+    int r = g_nccl.AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, h->comm, h->stream);
+    if (r != 0)
+        return fail(h, PRMF_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    return PRMF_OK;
+}
+
+int ensure_obj_capacity(prmf_handle* h, int n_steps) {
+    if (n_steps <= h->obj_capacity) return PRMF_OK;
+    if (h->obj) cudaFree(h->obj);
+    int cap = std::max(n_steps, 64);
+    int rc = dalloc(h, &h->obj, (size_t)cap * kObjStride);
+    if (rc) return rc;
+    h->obj_capacity = cap;
+    return PRMF_OK;
+}
+
+cudaEvent_t get_event(prmf_handle* h, int* idx) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->ev_pool.push_back(e);
+    *idx = (int)h->ev_pool.size() - 1;
+    return e;
+}
+
+void harvest_events(prmf_handle* h) {
+    for (auto& pr : h->ev_pairs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev_pool[pr.second], h->ev_pool[pr.second + 1]) == cudaSuccess) {
+            if (pr.first == 0) { h->xv_ms += ms; h->xv_n++; } else { h->xtu_ms += ms; h->xtu_n++; }
+        }
+    }
+    for (auto e : h->ev_pool) cudaEventDestroy(e);
+    h->ev_pool.clear();
+    h->ev_pairs.clear();
+}
+
+int enqueue_steps(prmf_handle* h, int n_steps, double gamma, double delta, double tradeoff) {
+    if (!h->have_X || !h->have_UV || !h->have_pw || !h->have_active)
+        return fail(h, PRMF_ERR_STATE, "prmf_step needs X, U/V, pathways and the active set first");
+    if (n_steps <= 0) return fail(h, PRMF_ERR_ARG, "n_steps must be positive");
+    CU(cudaSetDevice(h->device));
+    int rc = ensure_obj_capacity(h, n_steps);
+    if (rc) return rc;
+    if ((rc = ensure_pos(h))) return rc;
+    const double gdh[2] = {gamma, delta};
+    CU(cudaMemcpyAsync(h->gd, gdh, sizeof gdh, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(h->step_counter, 0, sizeof(int), h->stream));
+    const int64_t nk = h->n * h->k;
+    const int kk2 = h->k * h->k;
+    const size_t red_count = (size_t)nk + kk2 + 2;
+    for (int s = 0; s < n_steps; ++s) {
+        int i0 = 0, i1 = 0;
+        if (h->profiling) { cudaEvent_t e0 = get_event(h, &i0); get_event(h, &i1); cudaEventRecord(e0, h->stream); }
+        if ((rc = launch_xv(h))) return rc;
+        if (h->profiling) { cudaEventRecord(h->ev_pool[i0 + 1], h->stream); h->ev_pairs.push_back({0, i0}); }
+        if ((rc = launch_u_update(h))) return rc;
+        if (h->profiling) { cudaEvent_t e0 = get_event(h, &i0); get_event(h, &i1); cudaEventRecord(e0, h->stream); }
+        if ((rc = launch_xtu(h))) return rc;
+        if (h->profiling) { cudaEventRecord(h->ev_pool[i0 + 1], h->stream); h->ev_pairs.push_back({1, i0}); }
+        reduce_pack_kernel<<<(unsigned)((nk + kk2 + 255) / 256), 256, 0, h->stream>>>(
+            h->Bpart, h->chunks, nk, h->Gu_part, h->uu_grid, h->k, h->red);
+        LAUNCH_CHECK("reduce_pack_kernel");
+        if ((rc = allreduce(h, h->red, red_count))) return rc;
+        fro_from_gram_kernel<<<1, 32, 0, h->stream>>>(h->red, nk, h->k);
+        LAUNCH_CHECK("fro_from_gram_kernel");
+        if ((rc = launch_v_update(h))) return rc;
+        objective_kernel<<<1, 1024, obj_smem(h), h->stream>>>(h->V, (int)h->n, h->k, h->red, h->Gv_part, h->VB_part,
+                                                              h->vu_grid, h->normX_sq, h->pw, h->active, h->Gv,
+                                                              h->gd, tradeoff, h->obj, h->step_counter,
+                                                              h->obj_capacity);
+        LAUNCH_CHECK("objective_kernel");
+    }
+    return PRMF_OK;
+}
+
+int collect(prmf_handle* h, int n_steps, double* obj_parts, double* gamma_delta_out) {
+    CU(cudaSetDevice(h->device));
+    if (n_steps > h->obj_capacity) return fail(h, PRMF_ERR_ARG, "collect: more steps than were run");
+    if (obj_parts)
+        CU(cudaMemcpyAsync(obj_parts, h->obj, sizeof(double) * n_steps * kObjStride, cudaMemcpyDeviceToHost, h->stream));
+    if (gamma_delta_out)
+        CU(cudaMemcpyAsync(gamma_delta_out, h->gd, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->profiling) harvest_events(h);
+    return PRMF_OK;
+}
+
+int finish_X(prmf_handle* h) {
+    // ||X||^2 partial of this rank, all-reduced once
+    const int blocks = h->sm_count * 4;
+    if (h->m > 0) {
+        sumsq_kernel<<<blocks, 256, 0, h->stream>>>(h->X, h->ldx, h->m, h->n2, h->scal_part);
+        LAUNCH_CHECK("sumsq_kernel");
+        sum_partials_kernel<<<1, 256, 0, h->stream>>>(h->scal_part, blocks, h->normX_sq);
+        LAUNCH_CHECK("sum_partials_kernel");
+    } else {
+        CU(cudaMemsetAsync(h->normX_sq, 0, sizeof(double), h->stream));
+    }
+    int rc = allreduce(h, h->normX_sq, 1);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    h->have_X = true;
+    return PRMF_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int prmf_abi_version(void) { return 1; }
+
+const char* prmf_last_error(const prmf_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global, int64_t n, int k, void* stream) {
+    prmf_handle* h = nullptr;
+    if (!out) return fail(h, PRMF_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (m_local < 0 || n <= 0 || k <= 0 || m_global < m_local)
+        return fail(h, PRMF_ERR_ARG, "bad shape m_local=%lld m_global=%lld n=%lld k=%d", (long long)m_local,
+                    (long long)m_global, (long long)n, k);
+    if (k > 128) return fail(h, PRMF_ERR_ARG, "k=%d not supported (max 128)", k);
+    if (n > (int64_t)1 << 30) return fail(h, PRMF_ERR_ARG, "n too large");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(h, PRMF_ERR_CUDA, "no CUDA device (%s); libprmf_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= ndev) return fail(h, PRMF_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(h, PRMF_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(h, PRMF_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major < 10)
+        return fail(h, PRMF_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    prmf_handle* hh = new prmf_handle();
+    h = hh;
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->m = m_local; h->m_global = m_global; h->n = n; h->k = k;
+    h->ldx = round_up(n, 16);        // rows start on 128-byte lines; pad columns are zero
+    h->ldvt = round_up(n, 16);
+    h->n2 = (int)round_up(n, 2);
+    if (stream) { h->stream = (cudaStream_t)stream; }
+    else {
+        e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete hh; return fail(nullptr, PRMF_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+        h->own_stream = true;
+    }
+    // launch geometry
+    h->ktile = pick_ktile(k);
+    h->nq = pick_nq(k);
+    h->xv_grid = h->sm_count * 2;
+    h->uu_rows = (int)std::max<int64_t>(8, std::min<int64_t>(128, 4096 / k));
+    h->uu_grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count * 2, (m_local + h->uu_rows - 1) / h->uu_rows));
+    h->vu_rows = (int)std::max<int64_t>(8, std::min<int64_t>(32, 4096 / k));
+    h->vu_grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count * 2, (n + h->vu_rows - 1) / h->vu_rows));
+    h->panels = (int)((n + 1023) / 1024);
+    h->panel_w = (int)round_up((n + h->panels - 1) / h->panels, 4);
+    h->chunks = std::max(1, (h->sm_count * 2) / h->panels);
+    if (m_local > 0) h->chunks = (int)std::min<int64_t>(h->chunks, std::max<int64_t>(1, m_local / 8));
+    h->rows_per_chunk = std::max<int64_t>(1, (m_local + h->chunks - 1) / h->chunks);
+
+    int rc = 0;
+    const int64_t nk = n * k;
+    const int kk2 = k * k;
+#define ALLOC(ptr, count) if (!rc) rc = dalloc(h, &ptr, (size_t)(count))
+    ALLOC(h->X, (size_t)std::max<int64_t>(1, m_local) * h->ldx);
+    ALLOC(h->U, std::max<int64_t>(1, m_local) * k);
+    ALLOC(h->Ub, std::max<int64_t>(1, m_local) * k);
+    ALLOC(h->A, std::max<int64_t>(1, m_local) * k);
+    ALLOC(h->V, nk); ALLOC(h->Vb, nk); ALLOC(h->Vt, (size_t)k * h->ldvt);
+    ALLOC(h->Gv, kk2); ALLOC(h->Gvb, kk2);
+    ALLOC(h->Gu_part, (size_t)h->uu_grid * kk2);
+    ALLOC(h->Gv_part, (size_t)h->vu_grid * kk2);
+    ALLOC(h->VB_part, h->vu_grid);
+    ALLOC(h->Bpart, (size_t)h->chunks * nk);
+    ALLOC(h->red, (size_t)nk + kk2 + 2);
+    ALLOC(h->normX_sq, 1);
+    ALLOC(h->scal_part, (size_t)h->sm_count * 8);
+    ALLOC(h->gd, 2);
+    ALLOC(h->step_counter, 1);
+    ALLOC(h->active, k);
+    ALLOC(h->pos, nk);
+#undef ALLOC
+    if (!rc) {
+        cudaMemsetAsync(h->Vt, 0, sizeof(double) * k * h->ldvt, h->stream);
+        cudaMemsetAsync(h->red, 0, sizeof(double) * (nk + kk2 + 2), h->stream);
+        cudaMemsetAsync(h->Gu_part, 0, sizeof(double) * h->uu_grid * kk2, h->stream);
+        e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(h, PRMF_ERR_CUDA, "init memset: %s", cudaGetErrorString(e));
+    }
+    // opt in to large dynamic shared memory where k needs it
+    if (!rc) {
+        NQ_SWITCH(h->nq, {
+            if (!rc) rc = set_smem(h, u_update_kernel<NQ>, uu_smem(h));
+            if (!rc) rc = set_smem(h, v_update_kernel<NQ>, vu_smem(h));
+            if (!rc) rc = set_smem(h, gram_rows_kernel<NQ>, gram_smem(h));
+        });
+        if (!rc) rc = set_smem(h, objective_kernel, obj_smem(h));
+    }
+    if (rc) {
+        g_create_error = h->err;
+        prmf_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return PRMF_OK;
+}
+
+int prmf_destroy(prmf_handle* h) {
+    if (!h) return PRMF_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    harvest_events(h);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    void* bufs[] = {h->own_X ? h->X : nullptr, h->U, h->V, h->Vt, h->Ub, h->Vb, h->Gvb, h->A, h->Gv, h->Gu_part,
+                    h->Gv_part, h->VB_part, h->Bpart, h->red, h->normX_sq, h->scal_part, h->gd, h->obj,
+                    h->step_counter, h->active, h->pos};
+    for (void* b : bufs) if (b) cudaFree(b);
+    for (void* b : h->pw_allocs) cudaFree(b);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return PRMF_OK;
+}
+
+int prmf_set_X(prmf_handle* h, const double* X_host, int64_t ld) {
+    if (!h) return PRMF_ERR_ARG;
+    if ((!X_host && h->m > 0) || ld < h->n) return fail(h, PRMF_ERR_ARG, "prmf_set_X: bad pointer or ld < n");
+    CU(cudaSetDevice(h->device));
+    if (h->m > 0) {
+        CU(cudaMemsetAsync(h->X, 0, sizeof(double) * h->m * h->ldx, h->stream));
+        CU(cudaMemcpy2DAsync(h->X, h->ldx * sizeof(double), X_host, ld * sizeof(double), h->n * sizeof(double),
+                             h->m, cudaMemcpyHostToDevice, h->stream));
+    }
+    return finish_X(h);
+}
+
+int prmf_set_X_device(prmf_handle* h, const double* X_dev, int64_t ld) {
+    if (!h) return PRMF_ERR_ARG;
+    if ((!X_dev && h->m > 0) || ld < h->n) return fail(h, PRMF_ERR_ARG, "prmf_set_X_device: bad pointer or ld < n");
+    CU(cudaSetDevice(h->device));
+    if (h->m > 0) {
+        CU(cudaMemsetAsync(h->X, 0, sizeof(double) * h->m * h->ldx, h->stream));
+        CU(cudaMemcpy2DAsync(h->X, h->ldx * sizeof(double), X_dev, ld * sizeof(double), h->n * sizeof(double),
+                             h->m, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return finish_X(h);
+}
+
+int prmf_get_normX_sq(prmf_handle* h, double* out) {
+    if (!h || !out) return PRMF_ERR_ARG;
+    if (!h->have_X) return fail(h, PRMF_ERR_STATE, "X not set");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(out, h->normX_sq, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return PRMF_OK;
+}
+
+int prmf_set_pathways(prmf_handle* h, int32_t P, const int64_t* path_ptr, const int32_t* support_idx,
+                      const int64_t* row_ptr, const int32_t* col_local, const double* w) {
+    if (!h) return PRMF_ERR_ARG;
+    if (P <= 0 || !path_ptr || !row_ptr) return fail(h, PRMF_ERR_ARG, "prmf_set_pathways: P <= 0 or NULL tables");
+    const int64_t S = path_ptr[P];
+    if (path_ptr[0] != 0 || S < 0) return fail(h, PRMF_ERR_ARG, "path_ptr must start at 0");
+    const int64_t E = row_ptr[S];
+    if ((S > 0 && !support_idx) || (E > 0 && (!col_local || !w))) return fail(h, PRMF_ERR_ARG, "NULL pathway arrays");
+    // validate + derive deg, diag(L), diag(L)^-1/2 on the host (pow(x,-0.5) as numpy does, :58-62)
+    std::vector<double> deg(S, 0.0), ldiag(S, 0.0), isd(S, 0.0);
+    for (int32_t p = 0; p < P; ++p) {
+        const int64_t beg = path_ptr[p], end = path_ptr[p + 1];
+        if (end < beg) return fail(h, PRMF_ERR_ARG, "path_ptr not monotone at pathway %d", p);
+        const int64_t sp = end - beg;
+        for (int64_t r = beg; r < end; ++r) {
+            if (support_idx[r] < 0 || support_idx[r] >= h->n)
+                return fail(h, PRMF_ERR_ARG, "support index %d out of range at row %lld", support_idx[r], (long long)r);
+            if (row_ptr[r + 1] < row_ptr[r]) return fail(h, PRMF_ERR_ARG, "row_ptr not monotone at row %lld", (long long)r);
+            double d = 0.0, self = 0.0;
+            for (int64_t e2 = row_ptr[r]; e2 < row_ptr[r + 1]; ++e2) {
+                if (col_local[e2] < 0 || col_local[e2] >= sp)
+                    return fail(h, PRMF_ERR_ARG, "col_local out of range at entry %lld", (long long)e2);
+                d += w[e2];
+                if (beg + col_local[e2] == r) self += w[e2];
+            }
+            deg[r] = d;
+            ldiag[r] = d - self;
+            isd[r] = ldiag[r] != 0.0 ? std::pow(ldiag[r], -0.5) : 0.0;
+        }
+    }
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    for (void* b : h->pw_allocs) cudaFree(b);
+    h->pw_allocs.clear();
+    int rc = 0;
+    auto up = [&](const void* src, size_t bytes, const void** dst) -> int {
+        void* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, bytes ? bytes : 8);
+        if (e != cudaSuccess) return fail(h, PRMF_ERR_NOMEM, "cudaMalloc pathways: %s", cudaGetErrorString(e));
+        h->pw_allocs.push_back(d);
+        if (bytes) {
+            e = cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, h->stream);
+            if (e != cudaSuccess) return fail(h, PRMF_ERR_CUDA, "copy pathways: %s", cudaGetErrorString(e));
+        }
+        *dst = d;
+        return 0;
+    };
+    Pathways pw{};
+    pw.P = P;
+    if (!rc) rc = up(path_ptr, sizeof(int64_t) * (P + 1), (const void**)&pw.path_ptr);
+    if (!rc) rc = up(support_idx, sizeof(int32_t) * S, (const void**)&pw.support_idx);
+    if (!rc) rc = up(row_ptr, sizeof(int64_t) * (S + 1), (const void**)&pw.row_ptr);
+    if (!rc) rc = up(col_local, sizeof(int32_t) * E, (const void**)&pw.col_local);
+    if (!rc) rc = up(w, sizeof(double) * E, (const void**)&pw.w);
+    if (!rc) rc = up(deg.data(), sizeof(double) * S, (const void**)&pw.deg);
+    if (!rc) rc = up(ldiag.data(), sizeof(double) * S, (const void**)&pw.ldiag);
+    if (!rc) rc = up(isd.data(), sizeof(double) * S, (const void**)&pw.isd);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    h->pw = pw; h->S = S; h->E = E;
+    h->path_ptr_host.assign(path_ptr, path_ptr + P + 1);
+    h->have_pw = true;
+    h->have_active = false;
+    h->pos_dirty = true;
+    return PRMF_OK;
+}
+
+int prmf_set_UV(prmf_handle* h, const double* U_local, const double* V) {
+    if (!h) return PRMF_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    if (U_local && h->m > 0)
+        CU(cudaMemcpyAsync(h->U, U_local, sizeof(double) * h->m * h->k, cudaMemcpyHostToDevice, h->stream));
+    if (V) {
+        const int64_t nk = h->n * h->k;
+        CU(cudaMemcpyAsync(h->V, V, sizeof(double) * nk, cudaMemcpyHostToDevice, h->stream));
+        v_to_vt_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, h->stream>>>(h->V, (int)h->n, h->k, h->Vt, h->ldvt);
+        LAUNCH_CHECK("v_to_vt_kernel");
+        int rc = recompute_Gv(h);
+        if (rc) return rc;
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    if (V) h->have_UV = true;
+    return PRMF_OK;
+}
+
+int prmf_get_UV(prmf_handle* h, double* U_local, double* V) {
+    if (!h) return PRMF_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    if (U_local && h->m > 0)
+        CU(cudaMemcpyAsync(U_local, h->U, sizeof(double) * h->m * h->k, cudaMemcpyDeviceToHost, h->stream));
+    if (V) CU(cudaMemcpyAsync(V, h->V, sizeof(double) * h->n * h->k, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return PRMF_OK;
+}
+
+int prmf_set_active(prmf_handle* h, const int32_t* pathway_of_factor) {
+    if (!h || !pathway_of_factor) return PRMF_ERR_ARG;
+    if (!h->have_pw) return fail(h, PRMF_ERR_STATE, "pathways not set");
+    for (int c = 0; c < h->k; ++c)
+        if (pathway_of_factor[c] < 0 || pathway_of_factor[c] >= h->pw.P)
+            return fail(h, PRMF_ERR_ARG, "active pathway %d of factor %d out of range", pathway_of_factor[c], c);
+    CU(cudaSetDevice(h->device));
+    h->active_host.assign(pathway_of_factor, pathway_of_factor + h->k);
+    CU(cudaMemcpyAsync(h->active, h->active_host.data(), sizeof(int32_t) * h->k, cudaMemcpyHostToDevice, h->stream));
+    h->have_active = true;
+    h->pos_dirty = true;
+    return PRMF_OK;
+}
+
+int prmf_step_async(prmf_handle* h, int n_steps, double gamma, double delta, double tradeoff) {
+    if (!h) return PRMF_ERR_ARG;
+    return enqueue_steps(h, n_steps, gamma, delta, tradeoff);
+}
+
+int prmf_step_collect(prmf_handle* h, int n_steps, double* obj_parts, double* gamma_delta_out) {
+    if (!h) return PRMF_ERR_ARG;
+    return collect(h, n_steps, obj_parts, gamma_delta_out);
+}
+
+int prmf_step(prmf_handle* h, int n_steps, double gamma, double delta, double tradeoff, double* obj_parts,
+              double* gamma_delta_out) {
+    if (!h) return PRMF_ERR_ARG;
+    int rc = enqueue_steps(h, n_steps, gamma, delta, tradeoff);
+    if (rc) return rc;
+    return collect(h, n_steps, obj_parts, gamma_delta_out);
+}
+
+int prmf_scores(prmf_handle* h, double* mass, double* quad_norm, double* quad_raw) {
+    if (!h) return PRMF_ERR_ARG;
+    if (!h->have_pw || !h->have_UV) return fail(h, PRMF_ERR_STATE, "prmf_scores needs pathways and V");
+    CU(cudaSetDevice(h->device));
+    const size_t cnt = (size_t)h->k * h->pw.P;
+    double* d = nullptr;
+    int rc = dalloc(h, &d, cnt * 3);
+    if (rc) return rc;
+    scores_kernel<<<std::min(h->pw.P, h->sm_count * 8), 256, 0, h->stream>>>(h->V, h->k, h->Gv, h->pw, d, d + cnt, d + 2 * cnt);
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && mass) e = cudaMemcpyAsync(mass, d, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && quad_norm) e = cudaMemcpyAsync(quad_norm, d + cnt, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && quad_raw) e = cudaMemcpyAsync(quad_raw, d + 2 * cnt, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(h, PRMF_ERR_CUDA, "prmf_scores: %s", cudaGetErrorString(e));
+    return PRMF_OK;
+}
+
+int prmf_snapshot_best(prmf_handle* h) {
+    if (!h) return PRMF_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    if (h->m > 0) CU(cudaMemcpyAsync(h->Ub, h->U, sizeof(double) * h->m * h->k, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->Vb, h->V, sizeof(double) * h->n * h->k, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->Gvb, h->Gv, sizeof(double) * h->k * h->k, cudaMemcpyDeviceToDevice, h->stream));
+    return PRMF_OK;
+}
+
+int prmf_restore_best(prmf_handle* h) {
+    if (!h) return PRMF_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    if (h->m > 0) CU(cudaMemcpyAsync(h->U, h->Ub, sizeof(double) * h->m * h->k, cudaMemcpyDeviceToDevice, h->stream));
+    const int64_t nk = h->n * h->k;
+    CU(cudaMemcpyAsync(h->V, h->Vb, sizeof(double) * nk, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->Gv, h->Gvb, sizeof(double) * h->k * h->k, cudaMemcpyDeviceToDevice, h->stream));
+    v_to_vt_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, h->stream>>>(h->V, (int)h->n, h->k, h->Vt, h->ldvt);
+    LAUNCH_CHECK("v_to_vt_kernel");
+    CU(cudaStreamSynchronize(h->stream));
+    return PRMF_OK;
+}
+
+int prmf_residual_sq(prmf_handle* h, double* out) {
+    if (!h || !out) return PRMF_ERR_ARG;
+    if (!h->have_X || !h->have_UV) return fail(h, PRMF_ERR_STATE, "prmf_residual_sq needs X and U/V");
+    CU(cudaSetDevice(h->device));
+    const int blocks = h->sm_count * 4;
+    double* d = nullptr;
+    int rc = dalloc(h, &d, 1);
+    if (rc) return rc;
+    if (h->m > 0) {
+        residual_kernel<<<blocks, 256, 0, h->stream>>>(h->X, h->ldx, h->m, (int)h->n, h->U, h->V, h->k, h->scal_part);
+        h->launches++;
+        sum_partials_kernel<<<1, 256, 0, h->stream>>>(h->scal_part, blocks, d);
+        h->launches++;
+    } else {
+        cudaMemsetAsync(d, 0, sizeof(double), h->stream);
+    }
+    rc = allreduce(h, d, 1);
+    cudaError_t e = cudaGetLastError();
+    if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(out, d, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(h, PRMF_ERR_CUDA, "prmf_residual_sq: %s", cudaGetErrorString(e));
+    return PRMF_OK;
+}
+
+int prmf_nccl_load(const char* libnccl_path) {
+    const char* err = g_nccl.load(libnccl_path);
+    if (err) return fail(nullptr, PRMF_ERR_NCCL, "%s", err);
+    return PRMF_OK;
+}
+
+int prmf_comm_unique_id(uint8_t* id_out) {
+    if (!id_out) return PRMF_ERR_ARG;
+    if (!g_nccl.loaded()) return fail(nullptr, PRMF_ERR_NCCL, "call prmf_nccl_load first");
+    NcclUniqueId id;
+    int r = g_nccl.GetUniqueId(&id);
+    if (r != 0) return fail(nullptr, PRMF_ERR_NCCL, "ncclGetUniqueId failed (%d)", r);
+    memcpy(id_out, id.internal, PRMF_UNIQUE_ID_BYTES);
+    return PRMF_OK;
+}
+
+int prmf_comm_init(prmf_handle* h, int rank, int nranks, const uint8_t* id) {
+    if (!h || !id) return PRMF_ERR_ARG;
+    if (!g_nccl.loaded()) return fail(h, PRMF_ERR_NCCL, "call prmf_nccl_load first");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(h, PRMF_ERR_ARG, "bad rank %d / %d", rank, nranks);
+    CU(cudaSetDevice(h->device));
+    NcclUniqueId uid;
+    memcpy(uid.internal, id, PRMF_UNIQUE_ID_BYTES);
+    int r = g_nccl.CommInitRank(&h->comm, nranks, uid, rank);
+    if (r != 0) {
+        h->comm = nullptr;
+        return fail(h, PRMF_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    }
+    h->rank = rank; h->nranks = nranks;
+    return PRMF_OK;
+}
+
+int64_t prmf_launch_count(const prmf_handle* h) { return h ? h->launches : 0; }
+
+int prmf_set_profiling(prmf_handle* h, int on) {
+    if (!h) return PRMF_ERR_ARG;
+    h->profiling = on != 0;
+    return PRMF_OK;
+}
+
+int prmf_kernel_times(prmf_handle* h, int reset, double* xv_ms, double* xtu_ms, int64_t* launches) {
+    if (!h) return PRMF_ERR_ARG;
+    if (xv_ms) *xv_ms = h->xv_ms;
+    if (xtu_ms) *xtu_ms = h->xtu_ms;
+    if (launches) { launches[0] = h->xv_n; launches[1] = h->xtu_n; }
+    if (reset) { h->xv_ms = h->xtu_ms = 0; h->xv_n = h->xtu_n = 0; }
+    return PRMF_OK;
+}
+
+void* prmf_stream(const prmf_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+}  // extern "C"

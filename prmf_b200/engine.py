@@ -1,0 +1,205 @@
+"""Device engine: one `prmf_handle` (include/prmf_b200.h) per GPU, driven through ctypes.
+
+The engine is the only thing the host solver (`prmf_b200.solver`) talks to for arithmetic.  It has no
+CPU implementation: constructing it without a CUDA device or without libprmf_b200.so raises.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .pathways import PackedPathways
+
+OBJ_KEYS = ("recon", "manifold", "ignore", "fro", "obj", "gamma", "delta", "recon_sq")
+
+
+def _f64(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+class CudaEngine:
+    """Owns the device-resident X row block, U, V, pathway tables and scratch of one rank."""
+
+    def __init__(self, m_local, m_global, n, k, device=0, stream=None):
+        self.lib = _lib.load()
+        self.m, self.m_global, self.n, self.k = int(m_local), int(m_global), int(n), int(k)
+        self.P = 0
+        h = ctypes.c_void_p()
+        rc = self.lib.prmf_create(ctypes.byref(h), int(device), self.m, self.m_global, self.n, self.k,
+                                  ctypes.c_void_p(stream) if stream else None)
+        if rc != 0:
+            msg = self.lib.prmf_last_error(None)
+            raise _lib.PrmfLibraryError("prmf_create failed (%d): %s" % (rc, msg.decode() if msg else "?"))
+        self.h = h
+        self._keep = None
+
+    # -- lifetime ------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.prmf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ck(self, rc):
+        _lib.check(self.lib, self.h, rc)
+
+    # -- data ----------------------------------------------------------------------------------------
+    def set_X(self, X):
+        """X: this rank's row block; a C-contiguous float64 numpy array (host) or a CUDA torch tensor."""
+        if hasattr(X, "is_cuda") and X.is_cuda:
+            import torch
+            if X.dtype != torch.float64 or X.dim() != 2 or X.stride(1) != 1:
+                raise ValueError("device X must be a 2-D float64 tensor with unit column stride")
+            if tuple(X.shape) != (self.m, self.n):
+                raise ValueError("X has shape %s, engine expects %s" % (tuple(X.shape), (self.m, self.n)))
+            torch.cuda.current_stream(X.device).synchronize()
+            self._ck(self.lib.prmf_set_X_device(self.h, ctypes.c_void_p(X.data_ptr()), int(X.stride(0))))
+            return
+        X = np.asarray(X)
+        if X.shape != (self.m, self.n):
+            raise ValueError("X has shape %s, engine expects %s" % (X.shape, (self.m, self.n)))
+        if X.dtype != np.float64 or X.strides[1] != 8 or X.strides[0] % 8 != 0:
+            X = _f64(X)
+        self._ck(self.lib.prmf_set_X(self.h, _ptr(X), X.strides[0] // 8 if self.m > 0 else self.n))
+
+    @property
+    def normX_sq(self):
+        out = ctypes.c_double()
+        self._ck(self.lib.prmf_get_normX_sq(self.h, ctypes.byref(out)))
+        return out.value
+
+    def set_pathways(self, packed):
+        if not isinstance(packed, PackedPathways):
+            raise TypeError("expected PackedPathways")
+        if packed.n != self.n:
+            raise ValueError("pathways were packed for n=%d, engine has n=%d" % (packed.n, self.n))
+        self._ck(self.lib.prmf_set_pathways(self.h, packed.P, _ptr(packed.path_ptr), _ptr(packed.support_idx),
+                                            _ptr(packed.row_ptr), _ptr(packed.col_local), _ptr(packed.w)))
+        self.P = packed.P
+
+    def set_UV(self, U=None, V=None):
+        if U is not None:
+            U = _f64(U)
+            if U.shape != (self.m, self.k):
+                raise ValueError("U has shape %s, expected %s" % (U.shape, (self.m, self.k)))
+        if V is not None:
+            V = _f64(V)
+            if V.shape != (self.n, self.k):
+                raise ValueError("V has shape %s, expected %s" % (V.shape, (self.n, self.k)))
+        self._ck(self.lib.prmf_set_UV(self.h, _ptr(U), _ptr(V)))
+
+    def get_UV(self, want_U=True, want_V=True):
+        U = np.empty((self.m, self.k)) if want_U else None
+        V = np.empty((self.n, self.k)) if want_V else None
+        self._ck(self.lib.prmf_get_UV(self.h, _ptr(U), _ptr(V)))
+        return U, V
+
+    def set_active(self, pathway_of_factor):
+        a = np.ascontiguousarray(pathway_of_factor, dtype=np.int32)
+        if a.shape != (self.k,):
+            raise ValueError("need one active pathway per factor")
+        self._ck(self.lib.prmf_set_active(self.h, _ptr(a)))
+
+    # -- compute -------------------------------------------------------------------------------------
+    def step(self, n_steps, gamma, delta, tradeoff=None):
+        """`n_steps` inner updates; returns (parts[n_steps, 8], gamma_next, delta_next)."""
+        parts = np.empty((n_steps, _lib.OBJ_STRIDE))
+        gd = np.empty(2)
+        t = -1.0 if tradeoff is None else float(tradeoff)
+        self._ck(self.lib.prmf_step(self.h, int(n_steps), float(gamma), float(delta), t, _ptr(parts), _ptr(gd)))
+        return parts, float(gd[0]), float(gd[1])
+
+    def step_async(self, n_steps, gamma, delta, tradeoff=None):
+        t = -1.0 if tradeoff is None else float(tradeoff)
+        self._ck(self.lib.prmf_step_async(self.h, int(n_steps), float(gamma), float(delta), t))
+
+    def step_collect(self, n_steps):
+        parts = np.empty((n_steps, _lib.OBJ_STRIDE))
+        gd = np.empty(2)
+        self._ck(self.lib.prmf_step_collect(self.h, int(n_steps), _ptr(parts), _ptr(gd)))
+        return parts, float(gd[0]), float(gd[1])
+
+    def scores(self):
+        """(mass, quad_norm, quad_raw), each k x P, from the current V."""
+        mass = np.empty((self.k, self.P)); qn = np.empty((self.k, self.P)); qr = np.empty((self.k, self.P))
+        self._ck(self.lib.prmf_scores(self.h, _ptr(mass), _ptr(qn), _ptr(qr)))
+        return mass, qn, qr
+
+    def snapshot_best(self):
+        self._ck(self.lib.prmf_snapshot_best(self.h))
+
+    def restore_best(self):
+        self._ck(self.lib.prmf_restore_best(self.h))
+
+    def residual_sq(self):
+        out = ctypes.c_double()
+        self._ck(self.lib.prmf_residual_sq(self.h, ctypes.byref(out)))
+        return out.value
+
+    # -- multi-GPU -----------------------------------------------------------------------------------
+    def attach_comm(self, rank, nranks, unique_id):
+        buf = (ctypes.c_uint8 * _lib.UNIQUE_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        self._ck(self.lib.prmf_comm_init(self.h, int(rank), int(nranks), buf))
+
+    # -- introspection -------------------------------------------------------------------------------
+    @property
+    def launch_count(self):
+        return int(self.lib.prmf_launch_count(self.h))
+
+    def set_profiling(self, on):
+        self._ck(self.lib.prmf_set_profiling(self.h, 1 if on else 0))
+
+    def kernel_times(self, reset=True):
+        a, b = ctypes.c_double(), ctypes.c_double()
+        n = (ctypes.c_int64 * 2)()
+        self._ck(self.lib.prmf_kernel_times(self.h, 1 if reset else 0, ctypes.byref(a), ctypes.byref(b), n))
+        return {"xv_ms": a.value, "xtu_ms": b.value, "xv_launches": int(n[0]), "xtu_launches": int(n[1])}
+
+    @property
+    def stream(self):
+        return self.lib.prmf_stream(self.h)
+
+
+def nccl_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it and ships it to the other ranks)."""
+    lib = _lib.load()
+    nccl_load()
+    buf = (ctypes.c_uint8 * _lib.UNIQUE_ID_BYTES)()
+    rc = lib.prmf_comm_unique_id(buf)
+    if rc != 0:
+        raise _lib.PrmfLibraryError("prmf_comm_unique_id failed: %s" % lib.prmf_last_error(None).decode())
+    return bytes(buf)
+
+
+def nccl_load():
+    """Bind the library to the NCCL instance torch already loaded (torch bundles libnccl.so.2)."""
+    import glob
+    import os
+    lib = _lib.load()
+    path = None
+    try:
+        import nvidia.nccl
+        cands = glob.glob(os.path.join(os.path.dirname(nvidia.nccl.__path__[0] + "/"), "lib", "libnccl.so*"))
+        if cands:
+            path = cands[0]
+    except Exception:
+        pass
+    rc = lib.prmf_nccl_load(path.encode() if path else None)
+    if rc != 0:
+        raise _lib.PrmfLibraryError("prmf_nccl_load failed: %s" % lib.prmf_last_error(None).decode())

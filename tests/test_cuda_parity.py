@@ -1,0 +1,178 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and against the fixtures
+recorded from the unmodified reference.  Tolerances (fp64): per-inner-step objective parts rel 1e-9,
+U/V rel 1e-7 over the first blocks and 1e-6 at return, assignments/candidate lists/iteration counts
+identical."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, load_golden
+from helpers import check_run_against_golden, oracle_block, run_product, seed_all
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_whole_loop_matches_reference_fixture(case):
+    g = load_golden(case)
+    U, V, od, trace, _ = run_product(g)
+    check_run_against_golden(g, U, V, od, trace)
+
+
+def _instance(m, n, k, P, seed, weighted=False, psize=12):
+    from prmf_b200 import synth
+    X, nodelist, Gs = synth.small_instance(m=m, n=n, k_true=min(3, P), n_pathways=P, pathway_size=psize,
+                                           seed=seed, weighted=weighted)
+    rng = np.random.Generator(np.random.PCG64(seed + 100))
+    U = 3 * (1 - rng.random((m, k)))
+    V = 3 * (1 - rng.random((n, k)))
+    active = [int(rng.integers(0, P)) for _ in range(k)]
+    return X, nodelist, Gs, U, V, active
+
+
+@pytest.mark.parametrize("m,n,k,P", [
+    (64, 256, 6, 8),       # aligned
+    (37, 131, 3, 5),       # odd n, m not a multiple of the row tile
+    (5, 33, 1, 3),         # tiny, k = 1
+    (130, 1030, 7, 9),     # n just above one gene panel
+    (200, 517, 10, 12),    # the benchmark's k
+    (96, 300, 12, 6),      # k > 10: two factor tiles
+    (70, 210, 17, 6),      # k > 16: pairs-per-thread > 1
+    (50, 120, 33, 4),      # larger k
+])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_inner_steps_match_oracle(m, n, k, P, weighted):
+    from prmf_b200 import nmf_manifold_vec_update
+    X, nodelist, Gs, U, V, active = _instance(m, n, k, P, seed=m + n + k, weighted=weighted)
+    gamma, delta = 2.5, 0.3
+    Uo, Vo, parts_o, _, _, _ = oracle_block(X, U, V, Gs, nodelist, active, 3, gamma, delta)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()) as out:
+        Ug, Vg, od = nmf_manifold_vec_update(X, U, V, Gs, active, n_steps=3, gamma=gamma, delta=delta,
+                                             nodelist=nodelist)
+    np.testing.assert_allclose(Ug, Uo, rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(Vg, Vo, rtol=1e-10, atol=1e-13)
+    lines = out.getvalue().strip().splitlines()
+    got_obj = [float(l.split()[1]) for l in lines]
+    np.testing.assert_allclose(got_obj, parts_o[:, 4], rtol=1e-10)
+    for key, col in (("recon", 0), ("manifold", 1), ("ignore", 2), ("fro", 3), ("obj", 4)):
+        np.testing.assert_allclose(od[key], parts_o[-1, col], rtol=1e-9, atol=1e-12)
+
+
+def test_tradeoff_feedback_matches_oracle():
+    from prmf_b200 import nmf_manifold_vec_update
+    X, nodelist, Gs, U, V, active = _instance(60, 200, 4, 7, seed=9, weighted=True)
+    Uo, Vo, parts_o, g2o, d2o, _ = oracle_block(X, U, V, Gs, nodelist, active, 5, 3.0, 0.2, tradeoff=0.4)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        Ug, Vg, od, g2, d2 = nmf_manifold_vec_update(X, U, V, Gs, active, n_steps=5, gamma=3.0, delta=0.2,
+                                                     tradeoff=0.4, nodelist=nodelist)
+    np.testing.assert_allclose(Ug, Uo, rtol=1e-9)
+    np.testing.assert_allclose(Vg, Vo, rtol=1e-9)
+    np.testing.assert_allclose([g2, d2], [g2o, d2o], rtol=1e-9)
+    np.testing.assert_allclose(od["obj"], parts_o[-1, 4], rtol=1e-9)
+
+
+def test_zero_over_zero_and_clamps():
+    """U rows of zeros stay zero (0/0 := 1, :422); V is clamped at float32 eps (:442-444)."""
+    from prmf_b200 import nmf_manifold_vec_update
+    X, nodelist, Gs, U, V, active = _instance(40, 90, 3, 4, seed=4)
+    U[3, :] = 0.0
+    U[7, 1] = 0.0
+    V[5, :] = 0.0
+    X[:, 11] = 0.0
+    Uo, Vo, parts_o, _, _, _ = oracle_block(X, U, V, Gs, nodelist, active, 2, 1.0, 1.0)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        Ug, Vg, od = nmf_manifold_vec_update(X, U, V, Gs, active, n_steps=2, nodelist=nodelist)
+    assert np.all(Ug[3] == 0.0) and np.all(Uo[3] == 0.0)
+    eps = np.finfo(np.float32).eps
+    assert Vg.min() >= eps
+    assert np.all(Vg[:, :][Vo == eps] == eps)
+    np.testing.assert_allclose(Ug, Uo, rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(Vg, Vo, rtol=1e-10, atol=1e-14)
+
+
+def test_score_tables_match_reference_vectors():
+    from prmf_b200 import latent_pathway_tables, find_mins, restrict
+    g = load_golden("kernel_vectors")
+    mass, qn, qr = latent_pathway_tables(g["V"], g["Gs"], g["nodelist"])
+    score = np.sqrt(mass) + (1 - qn)
+    np.testing.assert_allclose(score, g["score"], rtol=1e-12)
+    np.testing.assert_allclose(qn, g["quad_norm"], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(qr, g["quad_raw"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_array_equal(find_mins(g["V"], g["Gs"], g["nodelist"]), g["find_mins"])
+    K, P = score.shape
+    cands = {k: [(p, 1) for p in range(P)] for k in range(K)}
+    got = restrict(g["V"], g["Gs"], cands, g["nodelist"])
+    for k, lst in g["meta"]["restricted"].items():
+        assert [p for p, _ in got[int(k)]] == [p for p, _ in lst]
+
+
+def test_recon_identity_against_exact_residual():
+    """The pass-free identity ||X||^2 - 2<V,X^T U> + <U^T U, V^T V> equals the residual computed by an
+    explicit third pass over X."""
+    from prmf_b200 import CudaEngine, pack_pathways
+    X, nodelist, Gs, U, V, active = _instance(300, 700, 6, 8, seed=21)
+    with CudaEngine(300, 300, 700, 6) as eng:
+        eng.set_X(X); eng.set_pathways(pack_pathways(Gs, nodelist)); eng.set_UV(U, V); eng.set_active(active)
+        parts, _, _ = eng.step(4, 1.0, 1.0)
+        exact = eng.residual_sq()
+        np.testing.assert_allclose(parts[-1, 7], exact, rtol=1e-11)
+        Ug, Vg = eng.get_UV()
+        np.testing.assert_allclose(exact, np.linalg.norm(X - Ug @ Vg.T) ** 2, rtol=1e-11)
+        np.testing.assert_allclose(eng.normX_sq, np.sum(X * X), rtol=1e-13)
+
+
+def test_bitwise_deterministic():
+    g = load_golden("small_tradeoff")
+    a = run_product(g)
+    b = run_product(g)
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1], b[1])
+    assert a[3]["obj_parts"] == b[3]["obj_parts"]
+
+
+def test_error_behaviour():
+    from prmf_b200 import CudaEngine, nmf_pathway, pack_pathways
+    from prmf_b200._lib import PrmfLibraryError
+    X, nodelist, Gs, U, V, active = _instance(20, 50, 3, 4, seed=2)
+    with pytest.raises(ValueError):                     # :656-659
+        nmf_pathway(X, Gs, k_latent=3, nodelist=nodelist, U_init=np.ones((19, 3)), quiet=True)
+    with pytest.raises(ValueError):
+        nmf_pathway(X, Gs, k_latent=3, nodelist=nodelist, V_init=np.ones((50, 2)), quiet=True)
+    with CudaEngine(20, 20, 50, 3) as eng:
+        with pytest.raises(PrmfLibraryError):           # step before any data
+            eng.step(1, 1.0, 1.0)
+        eng.set_X(X); eng.set_pathways(pack_pathways(Gs, nodelist)); eng.set_UV(U, V)
+        with pytest.raises(PrmfLibraryError):
+            eng.set_active([0, 1, 99])                  # pathway id out of range
+    with pytest.raises(PrmfLibraryError):
+        CudaEngine(10, 10, 10, 500)                     # k too large
+
+
+def test_full_size_properties():
+    """BASELINE config 2 shape (37 032 x 6 750, k=10, 300 pathways): size-independent checks --
+    the recon identity against the explicit residual pass, ||X||^2 against numpy, X.V against a
+    row sample computed on the host, and the objective decreasing over a 10-step block."""
+    from prmf_b200 import CudaEngine, pack_pathways, synth
+    m, n, k, P = 37032, 6750, 10, 300
+    X, nodelist, Gs = synth.recount2_shape(m, n, P, seed=0)
+    rng = np.random.Generator(np.random.PCG64(5))
+    U = 3 * (1 - rng.random((m, k))); V = 3 * (1 - rng.random((n, k)))
+    packed = pack_pathways(Gs, nodelist)
+    active = list(range(k))
+    normX = np.linalg.norm(X)
+    with CudaEngine(m, m, n, k) as eng:
+        eng.set_X(X); eng.set_pathways(packed); eng.set_UV(U, V); eng.set_active(active)
+        np.testing.assert_allclose(np.sqrt(eng.normX_sq), normX, rtol=1e-13)
+        gamma, delta = normX / k, 10 / normX
+        parts, _, _ = eng.step(1, gamma, delta)
+        U1, V1 = eng.get_UV()
+        rows = rng.integers(0, m, size=64)
+        num = X[rows] @ V
+        den = U[rows] @ (V.T @ V) + U[rows]
+        np.testing.assert_allclose(U1[rows], U[rows] * num / den, rtol=1e-11)
+        np.testing.assert_allclose(parts[0, 3], np.sum(U1 * U1), rtol=1e-12)
+        parts, _, _ = eng.step(9, gamma, delta)
+        np.testing.assert_allclose(parts[-1, 7], eng.residual_sq(), rtol=1e-10)
+        assert np.all(np.diff(parts[:, 4]) < 0), "objective should decrease with fixed pathways"

@@ -231,12 +231,18 @@ def run_ours(a):
     eng.set_UV(U0, V0)
     full_cands = init_latent_to_pathway_data(a.k, packed.P)
 
+    host_t = [0.0]
+
     def outer_iteration():
+        t0 = time.perf_counter()
         active = sample_active(full_cands, a.k)
         eng.set_active(active)
+        t1 = time.perf_counter()
         parts, _, _ = eng.step(MODULUS, gamma, delta)
+        t2 = time.perf_counter()
         mass, qn, _ = eng.scores()
         restrict_from_tables(mass, qn, full_cands)
+        host_t[0] += (t1 - t0) + (time.perf_counter() - t2)
         return parts
 
     def sync_all():
@@ -255,10 +261,12 @@ def run_ours(a):
     eng.set_profiling(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    host_t[0] = 0.0
     for _ in range(a.steps):
         parts = outer_iteration()
     e1.record(stream)
     sync_all()
+    host_ms = host_t[0] * 1e3 / a.steps      # sampling + set_active + scores + restrict per outer iteration
     eng.set_profiling(False)
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
@@ -282,8 +290,8 @@ def run_ours(a):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     bytes_xv = m_local * a.n * 8 + a.n * a.k * 8 + m_local * a.k * 8
     bytes_xtu = m_local * a.n * 8 + m_local * a.k * 8 + a.n * a.k * 8
-    xv_ms = kt["xv_ms"] / max(1, kt["xv_launches"])
-    xtu_ms = kt["xtu_ms"] / max(1, kt["xtu_launches"])
+    phase_ms = {name: (tot / max(1, cnt)) for name, (tot, cnt) in kt.items()}
+    xv_ms, xtu_ms = phase_ms["xv"], phase_ms["xtu"]
     ach_xv = bytes_xv / (xv_ms * 1e-3) / 1e9 if xv_ms > 0 else 0.0
     ach_xtu = bytes_xtu / (xtu_ms * 1e-3) / 1e9 if xtu_ms > 0 else 0.0
     step_bytes = bytes_xv + bytes_xtu
@@ -297,7 +305,8 @@ def run_ours(a):
         "xtu": {"ms": xtu_ms, "GBps": ach_xtu, "frac": ach_xtu / peak, "bytes": bytes_xtu},
         "inner_step": {"ms": inner_ms, "bytes": step_bytes, "GBps": step_bytes / (inner_ms * 1e-3) / 1e9,
                        "frac": step_bytes / (inner_ms * 1e-3) / 1e9 / peak,
-                       "x_stream_share_of_step": (xv_ms + xtu_ms) / inner_ms if inner_ms > 0 else None},
+                       "x_stream_share_of_step": (xv_ms + xtu_ms) / inner_ms if inner_ms > 0 else None,
+                       "phase_ms": phase_ms, "host_ms_per_outer": host_ms},
     }
 
     # e2e: the same outer iteration with HOST buffers (pinned X, U, V in; U, V, objective out)

@@ -123,9 +123,11 @@ int prmf_comm_init(prmf_handle* h, int rank, int nranks, const uint8_t* id);
 /* ---- introspection used by bench.py and the tests ---------------------------------------------------*/
 /* Number of kernel launches issued by this handle so far. */
 int64_t prmf_launch_count(const prmf_handle* h);
-/* Device time (ms, CUDA events on the handle's stream) of the X.V pass and the X^T.U pass accumulated
- * since the last call with reset != 0; `launches` receives the number of timed launches of each. */
-int prmf_kernel_times(prmf_handle* h, int reset, double* xv_ms, double* xtu_ms, int64_t* launches);
+/* Device time (ms, CUDA events on the handle's stream) per phase of the inner step, accumulated since the
+ * last call with reset != 0, and the number of timed occurrences of each.  Phases (PRMF_N_PHASES):
+ * 0 pass 1 (X.V), 1 U update, 2 pass 2 (X^T.U), 3 partial sums + all-reduce, 4 V update, 5 objective. */
+#define PRMF_N_PHASES 6
+int prmf_kernel_times(prmf_handle* h, int reset, double* phase_ms, int64_t* phase_count);
 /* Enable (1) / disable (0) per-kernel event timing inside prmf_step (off by default). */
 int prmf_set_profiling(prmf_handle* h, int on);
 /* The cudaStream_t the handle launches on. */

@@ -8,6 +8,8 @@ LIB_PATH = os.path.join(HERE, "libprmf_b200.so")
 
 OBJ_STRIDE = 8
 UNIQUE_ID_BYTES = 128
+N_PHASES = 6
+PHASES = ("xv", "u_update", "xtu", "reduce", "v_update", "objective")
 
 # every symbol include/prmf_b200.h declares: name -> (restype, argtypes)
 _P = c_void_p
@@ -34,7 +36,7 @@ SYMBOLS = {
     "prmf_comm_unique_id": (c_int, [POINTER(c_uint8)]),
     "prmf_comm_init": (c_int, [_P, c_int, c_int, POINTER(c_uint8)]),
     "prmf_launch_count": (c_int64, [_P]),
-    "prmf_kernel_times": (c_int, [_P, c_int, POINTER(c_double), POINTER(c_double), POINTER(c_int64)]),
+    "prmf_kernel_times": (c_int, [_P, c_int, POINTER(c_double), POINTER(c_int64)]),
     "prmf_set_profiling": (c_int, [_P, c_int]),
     "prmf_stream": (_P, [_P]),
 }

@@ -24,6 +24,21 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// s = part[0] + part[stride] + ... (count terms, added in index order; loads issued 8 at a time)
+__device__ __forceinline__ double sum_strided(const double* __restrict__ part, int count, int64_t stride) {
+    double s = 0.0;
+    int c = 0;
+    for (; c + 8 <= count; c += 8) {
+        double t[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t[q] = part[(int64_t)(c + q) * stride];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s += t[q];
+    }
+    for (; c < count; ++c) s += part[(int64_t)c * stride];
+    return s;
+}
+
 // Deterministic block reduction (fixed tree); result valid in thread 0.  `scratch` holds >= 32 doubles.
 __device__ __forceinline__ double block_sum(double v, double* scratch) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -71,63 +86,8 @@ __global__ void sum_partials_kernel(const double* __restrict__ part, int count, 
 }
 
 // ----------------------------------------------------------------------------------------------------
-// Pass 1 over X:  A[:, k0:k0+KT] = X . V[:, k0:k0+KT]          (U_up_num, :420)
-// A warp owns RW consecutive rows; lanes stride along the genes (coalesced 128-bit streaming loads of X,
-// coalesced loads of the factor-major copy Vt which stays L1/L2 resident); one shuffle reduction per row.
-// ----------------------------------------------------------------------------------------------------
-template <int KT, int RW>
-__global__ void __launch_bounds__(256, 2)
-xv_kernel(const double* __restrict__ X, int64_t ldx, int64_t m, int n2, const double* __restrict__ Vt,
-          int64_t ldvt, int k0, int k, double* __restrict__ A) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const double* vt = Vt + (int64_t)k0 * ldvt;
-    for (int64_t row0 = warp * RW; row0 < m; row0 += nwarps * RW) {
-        const double* xr[RW];
-#pragma unroll
-        for (int r = 0; r < RW; ++r) {
-            int64_t row = row0 + r < m ? row0 + r : m - 1;     // tail rows recompute the last row
-            xr[r] = X + row * ldx;
-        }
-        double acc[RW][KT];
-#pragma unroll
-        for (int r = 0; r < RW; ++r)
-#pragma unroll
-            for (int c = 0; c < KT; ++c) acc[r][c] = 0.0;
-#pragma unroll 1
-        for (int j = lane * 2; j < n2; j += 64) {
-            double2 x[RW];
-#pragma unroll
-            for (int r = 0; r < RW; ++r) x[r] = ld_stream(xr[r] + j);
-#pragma unroll
-            for (int c = 0; c < KT; ++c) {
-                const double2 v = *reinterpret_cast<const double2*>(vt + (int64_t)c * ldvt + j);
-#pragma unroll
-                for (int r = 0; r < RW; ++r) {
-                    acc[r][c] = fma(x[r].x, v.x, acc[r][c]);
-                    acc[r][c] = fma(x[r].y, v.y, acc[r][c]);
-                }
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < RW; ++r)
-#pragma unroll
-            for (int c = 0; c < KT; ++c) acc[r][c] = warp_sum(acc[r][c]);
-        if (lane == 0) {
-#pragma unroll
-            for (int r = 0; r < RW; ++r)
-                if (row0 + r < m) {
-#pragma unroll
-                    for (int c = 0; c < KT; ++c) A[(row0 + r) * k + k0 + c] = acc[r][c];
-                }
-        }
-    }
-}
-
-// ----------------------------------------------------------------------------------------------------
 // U update (:421-422) + per-block partials of U^T U (:425).  sum(U^2) (:359) is its trace.
-//   den = U.Gv + U ; U <- U * (A / den  if den != 0 else 1)
+//   A = sum of the pass-1 partials ; den = U.Gv + U ; U <- U * (A / den  if den != 0 else 1)
 // Persistent blocks loop over row tiles; the tile of new U rows is staged in shared memory and every
 // thread accumulates its (a,b) pairs of the Gram matrix in registers across tiles.
 // ----------------------------------------------------------------------------------------------------
@@ -135,7 +95,7 @@ constexpr int kMaxPairsPerThread = 64;   // k <= 128 with 256 threads
 
 template <int NQ>
 __global__ void __launch_bounds__(256)
-u_update_kernel(double* __restrict__ U, const double* __restrict__ A, const double* __restrict__ Gv,
+u_update_kernel(double* __restrict__ U, const double* __restrict__ Apart, int achunks, const double* __restrict__ Gv,
                 int64_t m, int k, int rows_per_tile, double* __restrict__ Gu_part) {
     extern __shared__ double sm[];
     double* sGv = sm;                  // k*k
@@ -157,8 +117,8 @@ u_update_kernel(double* __restrict__ U, const double* __restrict__ A, const doub
             for (int l = 0; l < k; ++l) den = fma(urow[l], sGv[l * k + c], den);
             const double u = urow[c];
             den += u;
-            const double a = A[(r0 + r) * k + c];
-            const double f = (den != 0.0) ? a / den : 1.0;
+            const double a = sum_strided(Apart + (r0 + r) * k + c, achunks, m * k);      // X.V   (:420)
+            const double f = (den != 0.0) ? a / den : 1.0;                                  // 0/0 := 1 (:422)
             sU[e] = u * f;
         }
         __syncthreads();
@@ -183,36 +143,41 @@ u_update_kernel(double* __restrict__ U, const double* __restrict__ A, const doub
 }
 
 // ----------------------------------------------------------------------------------------------------
-// Pass 2 over X:  Bpart[chunk][:, k0:k0+KT] = X[rows of chunk]^T . U[rows of chunk, k0:k0+KT]   (:424)
-// A thread owns 4 consecutive genes (two 128-bit streaming loads per row) and KT accumulators for each;
-// the U row is the same for the whole block and comes from shared memory (broadcast).
+// The X-stream kernel, used for BOTH passes:   Out[chunk][j][k0:k0+KT] = sum_{i in chunk} M[i][j] * W[i][k0:k0+KT]
+//   pass 1  (U_up_num = X.V, :420):        M = Xt (genes x samples, the transposed copy), W = V -> A partials
+//   pass 2  (V_up_num_recon = X^T.U, :424): M = X  (samples x genes),                     W = U -> B partials
+// M is row-major with leading dimension ldm (a multiple of 16 doubles, pad columns zero).  A thread owns 4
+// consecutive columns of M (two 128-bit streaming loads per row, 8 rows in flight) and KT accumulators for
+// each; the W row is the same for the whole block and is read from shared memory as a broadcast.  The grid
+// is (column panels) x (row chunks); per-chunk partials are summed in a fixed order by the consumer.
 // ----------------------------------------------------------------------------------------------------
-constexpr int kXtuRowsPerStage = 32;
+constexpr int kSkinnyRowsPerStage = 32;
 
 template <int KT>
 __global__ void __launch_bounds__(256, 2)
-xtu_kernel(const double* __restrict__ X, int64_t ldx, int64_t m, int n, const double* __restrict__ U,
-           int k, int k0, int panel_w, int64_t rows_per_chunk, double* __restrict__ Bpart) {
-    __shared__ double sU[kXtuRowsPerStage][KT];
+skinny_tn_kernel(const double* __restrict__ M, int64_t ldm, int64_t rows_total, int64_t cols,
+                 const double* __restrict__ W, int k, int k0, int panel_w, int64_t rows_per_chunk,
+                 double* __restrict__ OutPart) {
+    __shared__ double sW[kSkinnyRowsPerStage][KT];
     const int panel = blockIdx.x;
     const int64_t chunk = blockIdx.y;
     const int jl = threadIdx.x * 4;
-    const int j0 = panel * panel_w + jl;
-    const bool active = (jl < panel_w) && (j0 < (int)ldx);
+    const int64_t j0 = (int64_t)panel * panel_w + jl;
+    const bool active = (jl < panel_w) && (j0 < ldm);
     const int64_t rbeg = chunk * rows_per_chunk;
-    const int64_t rend = min(m, rbeg + rows_per_chunk);
+    const int64_t rend = min(rows_total, rbeg + rows_per_chunk);
     double acc[4][KT];
 #pragma unroll
     for (int g = 0; g < 4; ++g)
 #pragma unroll
         for (int c = 0; c < KT; ++c) acc[g][c] = 0.0;
-    const double* xp = X + j0;
-    for (int64_t r0 = rbeg; r0 < rend; r0 += kXtuRowsPerStage) {
-        const int rows = (int)min((int64_t)kXtuRowsPerStage, rend - r0);
+    const double* xp = M + j0;
+    for (int64_t r0 = rbeg; r0 < rend; r0 += kSkinnyRowsPerStage) {
+        const int rows = (int)min((int64_t)kSkinnyRowsPerStage, rend - r0);
         __syncthreads();
         for (int e = threadIdx.x; e < rows * KT; e += blockDim.x) {
             const int r = e / KT, c = e - r * KT;
-            sU[r][c] = U[(r0 + r) * k + k0 + c];
+            sW[r][c] = W[(r0 + r) * k + k0 + c];
         }
         __syncthreads();
         if (active) {
@@ -221,7 +186,7 @@ xtu_kernel(const double* __restrict__ X, int64_t ldx, int64_t m, int n, const do
                 double2 xa[4], xb[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const double* p = xp + (r0 + r + q) * ldx;
+                    const double* p = xp + (r0 + r + q) * ldm;
                     xa[q] = ld_stream(p);
                     xb[q] = ld_stream(p + 2);
                 }
@@ -229,7 +194,7 @@ xtu_kernel(const double* __restrict__ X, int64_t ldx, int64_t m, int n, const do
                 for (int q = 0; q < 4; ++q)
 #pragma unroll
                     for (int c = 0; c < KT; ++c) {
-                        const double u = sU[r + q][c];
+                        const double u = sW[r + q][c];
                         acc[0][c] = fma(xa[q].x, u, acc[0][c]);
                         acc[1][c] = fma(xa[q].y, u, acc[1][c]);
                         acc[2][c] = fma(xb[q].x, u, acc[2][c]);
@@ -237,11 +202,11 @@ xtu_kernel(const double* __restrict__ X, int64_t ldx, int64_t m, int n, const do
                     }
             }
             for (; r < rows; ++r) {
-                const double* p = xp + (r0 + r) * ldx;
+                const double* p = xp + (r0 + r) * ldm;
                 const double2 xa = ld_stream(p), xb = ld_stream(p + 2);
 #pragma unroll
                 for (int c = 0; c < KT; ++c) {
-                    const double u = sU[r][c];
+                    const double u = sW[r][c];
                     acc[0][c] = fma(xa.x, u, acc[0][c]);
                     acc[1][c] = fma(xa.y, u, acc[1][c]);
                     acc[2][c] = fma(xb.x, u, acc[2][c]);
@@ -253,13 +218,33 @@ xtu_kernel(const double* __restrict__ X, int64_t ldx, int64_t m, int n, const do
     if (active) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-            const int j = j0 + g;
-            if (j < n) {
-                double* out = Bpart + ((int64_t)chunk * n + j) * k + k0;
+            const int64_t j = j0 + g;
+            if (j < cols) {
+                double* out = OutPart + ((int64_t)chunk * cols + j) * k + k0;
 #pragma unroll
                 for (int c = 0; c < KT; ++c) out[c] = acc[g][c];
             }
         }
+    }
+}
+
+// Xt[j][i] = X[i][j] : the factor of 2 in HBM capacity buys a coalesced, reduction-free pass 1.
+__global__ void __launch_bounds__(256)
+transpose_kernel(const double* __restrict__ X, int64_t ldx, int64_t m, int64_t n, double* __restrict__ Xt,
+                 int64_t ldxt) {
+    __shared__ double tile[32][33];
+    const int64_t i0 = (int64_t)blockIdx.y * 32, j0 = (int64_t)blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t i = i0 + r, j = j0 + tx;
+        tile[r][tx] = (i < m && j < n) ? X[i * ldx + j] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t j = j0 + r, i = i0 + tx;
+        if (j < n && i < m) Xt[j * ldxt + i] = tile[tx][r];
     }
 }
 
@@ -273,23 +258,11 @@ reduce_pack_kernel(const double* __restrict__ Bpart, int chunks, int64_t nk, con
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int kk2 = k * k;
     if (idx < nk) {
-        double s = 0.0;
-        for (int c = 0; c < chunks; ++c) s += Bpart[(int64_t)c * nk + idx];
-        red[idx] = s;
+        red[idx] = sum_strided(Bpart + idx, chunks, nk);
     } else if (idx < nk + kk2) {
-        const int e = (int)(idx - nk);
-        double s = 0.0;
-        for (int b = 0; b < gu_blocks; ++b) s += Gu_part[(int64_t)b * kk2 + e];
-        red[idx] = s;
-    }
-}
-
-// sum(U^2) = trace(U^T U); runs after the all-reduce so every rank derives it from identical data.
-__global__ void fro_from_gram_kernel(double* __restrict__ red, int64_t nk, int k) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double s = 0.0;
-        for (int a = 0; a < k; ++a) s += red[nk + a * k + a];
-        red[nk + k * k] = s;
+        red[idx] = sum_strided(Gu_part + (idx - nk), gu_blocks, kk2);
+    } else if (idx < nk + kk2 + 2) {
+        red[idx] = 0.0;
     }
 }
 
@@ -321,11 +294,13 @@ __global__ void build_pos_kernel(Pathways pw, const int32_t* __restrict__ active
 // V update (:425-444) + per-block partials of V_new^T V_new and sum(V_new * B).
 //   C = V.Gu ; num = B + (gamma*W v + delta*(v+1)^-2 on the support) ; den = C + gamma*deg*v
 //   den < eps -> eps ; V <- V*num/den ; V < eps -> eps
-// red = [B | Gu | fro] (after the all-reduce).  gd = {gamma, delta} on the device.
+// red = [B | Gu | .] (after the all-reduce).  gd = {gamma, delta} on the device.  V is double-buffered:
+// pathway neighbours of a gene may be updated by another block, so new values go to Vnew while every
+// block reads the untouched Vold.
 // ----------------------------------------------------------------------------------------------------
 template <int NQ>
 __global__ void __launch_bounds__(256)
-v_update_kernel(double* __restrict__ V, double* __restrict__ Vt, int64_t ldvt, const double* __restrict__ red,
+v_update_kernel(const double* __restrict__ Vold, double* __restrict__ Vnew, const double* __restrict__ red,
                 int n, int k, Pathways pw, const int32_t* __restrict__ active, const int32_t* __restrict__ pos,
                 const double* __restrict__ gd, int rows_per_tile, double* __restrict__ Gv_part,
                 double* __restrict__ VB_part) {
@@ -350,7 +325,7 @@ v_update_kernel(double* __restrict__ V, double* __restrict__ Vt, int64_t ldvt, c
         for (int e = threadIdx.x; e < rows * k; e += blockDim.x) {
             const int r = e / k, c = e - r * k;
             const int j = j0 + r;
-            const double* vrow = V + (int64_t)j * k;
+            const double* vrow = Vold + (int64_t)j * k;
             double cden = 0.0;
             for (int l = 0; l < k; ++l) cden = fma(vrow[l], sGu[l * k + c], cden);   // V.Gu   (:425)
             const double v = vrow[c];
@@ -361,7 +336,7 @@ v_update_kernel(double* __restrict__ V, double* __restrict__ Vt, int64_t ldvt, c
                 const int64_t base = pw.path_ptr[active[c]];
                 double wv = 0.0;
                 for (int64_t e2 = pw.row_ptr[pr]; e2 < pw.row_ptr[pr + 1]; ++e2)
-                    wv = fma(pw.w[e2], V[(int64_t)pw.support_idx[base + pw.col_local[e2]] * k + c], wv);
+                    wv = fma(pw.w[e2], Vold[(int64_t)pw.support_idx[base + pw.col_local[e2]] * k + c], wv);
                 const double vp1 = v + 1.0;
                 const double man = gamma * wv;                                          // :434
                 const double ign = delta * (1.0 / (vp1 * vp1));                         // :438
@@ -372,16 +347,10 @@ v_update_kernel(double* __restrict__ V, double* __restrict__ Vt, int64_t ldvt, c
             double vn = v * (num / den);                                                // :443
             if (vn < kEps) vn = kEps;                                                   // :444
             sV[e] = vn;
+            Vnew[(int64_t)j0 * k + e] = vn;
             vb = fma(vn, b, vb);
         }
         __syncthreads();
-        // Pathway neighbours of a gene may live in another block's tile, so the gene-major V must stay
-        // intact until every block is done: new values go to the factor-major copy Vt only, and
-        // vt_to_v_kernel refreshes V afterwards.
-        for (int e = threadIdx.x; e < rows * k; e += blockDim.x) {
-            const int r = e / k, c = e - r * k;
-            Vt[(int64_t)c * ldvt + j0 + r] = sV[e];
-        }
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
             const int pidx = threadIdx.x + q * 256;
@@ -401,27 +370,6 @@ v_update_kernel(double* __restrict__ V, double* __restrict__ Vt, int64_t ldvt, c
     }
     const double t = block_sum(vb, scratch);
     if (threadIdx.x == 0) VB_part[blockIdx.x] = t;
-}
-
-// V (gene-major, n x k) <- Vt (factor-major, k x ldvt): second half of the V update.  The update kernel
-// reads old V (own row and pathway neighbours in other tiles) and writes only Vt, so no block can see a
-// half-updated V.
-__global__ void __launch_bounds__(256)
-vt_to_v_kernel(const double* __restrict__ Vt, int64_t ldvt, int n, int k, double* __restrict__ V) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < (int64_t)n * k) {
-        const int j = (int)(idx / k), c = (int)(idx - (int64_t)j * k);
-        V[idx] = Vt[(int64_t)c * ldvt + j];
-    }
-}
-
-__global__ void __launch_bounds__(256)
-v_to_vt_kernel(const double* __restrict__ V, int n, int k, double* __restrict__ Vt, int64_t ldvt) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < (int64_t)n * k) {
-        const int j = (int)(idx / k), c = (int)(idx - (int64_t)j * k);
-        Vt[(int64_t)c * ldvt + j] = V[idx];
-    }
 }
 
 // Gram of V from scratch (after prmf_set_UV): same tiling as the update kernel so partial layout matches.
@@ -475,7 +423,10 @@ sum_gram_parts_kernel(const double* __restrict__ G_part, int blocks, int kk2, do
 // Objective of one inner step (:336-372) without a pass over X, and the tradeoff feedback (:542-548).
 //   recon^2 = ||X||^2 - 2 sum(V_new*B) + sum(Gu*Gv_new)        (B = X^T U_new, Gu = U_new^T U_new)
 //   manifold = sum_k vhat_k^T Lhat_{p_k} vhat_k ; ignore = sum_k sum_{i in supp} 1/(vhat_i + 1)
-// One block.  Also publishes Gv_new for the next step's U update.
+//   fro = trace(Gu) = sum(U^2)
+// One block of 32 warps.  Gv_new entries are summed from the V-update partials (a warp per entry, or a
+// thread per entry when k*k is large); a warp per factor walks the active pathway.  Also publishes
+// Gv_new for the next step's U update.
 // ----------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 objective_kernel(const double* __restrict__ V, int n, int k, const double* __restrict__ red,
@@ -484,30 +435,40 @@ objective_kernel(const double* __restrict__ V, int n, int k, const double* __res
                  double* __restrict__ Gv, double* __restrict__ gd, double tradeoff,
                  double* __restrict__ obj_out, int* __restrict__ step_counter, int obj_capacity) {
     extern __shared__ double sm[];
-    double* sGv = sm;        // k*k
+    double* sGv = sm;            // k*k
+    double* sMan = sm + k * k;   // k
+    double* sIgn = sMan + k;     // k
     __shared__ double scratch[32];
     const int kk2 = k * k;
     const int64_t nk = (int64_t)n * k;
-    double gg = 0.0;
-    for (int e = threadIdx.x; e < kk2; e += blockDim.x) {
-        double s = 0.0;
-        for (int b = 0; b < vblocks; ++b) s += Gv_part[(int64_t)b * kk2 + e];
-        sGv[e] = s;
-        Gv[e] = s;
-        gg = fma(s, red[nk + e], gg);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (kk2 <= 512) {
+        for (int e = warp; e < kk2; e += nw) {
+            double s = 0.0;
+            for (int b = lane; b < vblocks; b += 32) s += Gv_part[(int64_t)b * kk2 + e];
+            s = warp_sum(s);
+            if (lane == 0) { sGv[e] = s; Gv[e] = s; }
+        }
+    } else {
+        for (int e = threadIdx.x; e < kk2; e += blockDim.x) {
+            const double s = sum_strided(Gv_part + e, vblocks, kk2);
+            sGv[e] = s; Gv[e] = s;
+        }
     }
+    __syncthreads();
+    double gg = 0.0;
+    for (int e = threadIdx.x; e < kk2; e += blockDim.x) gg = fma(sGv[e], red[nk + e], gg);
     double vb = 0.0;
     for (int b = threadIdx.x; b < vblocks; b += blockDim.x) vb += VB_part[b];
     const double GG = block_sum(gg, scratch);
     const double VB = block_sum(vb, scratch);
-    __syncthreads();
-    // manifold / ignore: (factor, support row) pairs strided over the block
-    double man = 0.0, ign = 0.0;
-    for (int c = 0; c < k; ++c) {
+    // manifold / ignore: a warp per factor, lanes over the support rows of its active pathway
+    for (int c = warp; c < k; c += nw) {
         const int p = active[c];
         const int64_t beg = pw.path_ptr[p], end = pw.path_ptr[p + 1];
         const double nrm = sqrt(sGv[c * k + c]);
-        for (int64_t r = beg + threadIdx.x; r < end; r += blockDim.x) {
+        double man = 0.0, ign = 0.0;
+        for (int64_t r = beg + lane; r < end; r += 32) {
             const double vr = V[(int64_t)pw.support_idx[r] * k + c] / nrm;                 // :345
             const double ir = pw.isd[r];
             double y = (ir * (pw.ldiag[r] * ir)) * vr;                                      // diagonal of Lhat
@@ -520,14 +481,16 @@ objective_kernel(const double* __restrict__ V, int n, int k, const double* __res
             man = fma(y, vr, man);                                                          // :350
             ign += 1.0 / (vr + 1.0);                                                        // :352
         }
+        man = warp_sum(man); ign = warp_sum(ign);
+        if (lane == 0) { sMan[c] = man; sIgn[c] = ign; }
     }
-    const double MAN = block_sum(man, scratch);
-    const double IGN = block_sum(ign, scratch);
+    __syncthreads();
     if (threadIdx.x == 0) {
+        double MAN = 0.0, IGN = 0.0, fro = 0.0;
+        for (int c = 0; c < k; ++c) { MAN += sMan[c]; IGN += sIgn[c]; fro += red[nk + c * k + c]; }   // :359
         const double gamma = gd[0], delta = gd[1];
-        double r2 = normX_sq[0] - 2.0 * VB + GG;
+        const double r2 = normX_sq[0] - 2.0 * VB + GG;
         const double recon = sqrt(r2 > 0.0 ? r2 : 0.0);
-        const double fro = red[nk + kk2];
         const double obj = recon + gamma * MAN + delta * IGN + fro;                         // :362
         const int s = *step_counter;
         if (s < obj_capacity) {

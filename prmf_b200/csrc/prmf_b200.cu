@@ -1,15 +1,13 @@
 // libprmf_b200.so -- C ABI (include/prmf_b200.h) over the sm_100a kernels in kernels.cuh.
 // Host orchestration of one PRMF inner step (reference prmf_runner.py:419-449):
 //
-//   xv_kernel           A  = X.V                       pass 1 over X          (:420)
-//   u_update_kernel     U <- U*A/(U.Gv+U), Gu partials                        (:421-422,:425)
-//   xtu_kernel          B partials = X^T.U_new         pass 2 over X          (:424)
+//   skinny_tn_kernel    A partials = Xt^T.V            pass 1 over X (transposed copy)   (:420)
+//   u_update_kernel     U <- U*A/(U.Gv+U), Gu partials                                   (:421-422,:425)
+//   skinny_tn_kernel    B partials = X^T.U_new         pass 2 over X                     (:424)
 //   reduce_pack_kernel  red = [B | Gu | .]  (fixed-order sums)
 //   ncclAllReduce(red)                                 only with a communicator
-//   fro_from_gram       red[..] = trace(Gu) = sum(U^2)                        (:359)
-//   v_update_kernel     V_new (factor-major copy), Gv/VB partials             (:425-444)
-//   vt_to_v_kernel      gene-major V refreshed
-//   objective_kernel    Gv_new, recon/manifold/ignore/fro/obj, tradeoff       (:336-372,:542-548)
+//   v_update_kernel     V_new (double-buffered), Gv/VB partials                          (:425-444)
+//   objective_kernel    Gv_new, recon/manifold/ignore/fro/obj, tradeoff                  (:336-372,:542-548)
 #include "../../include/prmf_b200.h"
 
 #include <cmath>
@@ -41,17 +39,17 @@ struct prmf_handle {
     int sm_count = 148;
     int64_t m = 0, m_global = 0, n = 0;
     int k = 0;
-    int64_t ldx = 0, ldvt = 0;
+    int64_t ldx = 0, ldxt = 0;
     int n2 = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     std::string err;
 
     // device buffers
-    double* X = nullptr;
-    bool own_X = true;
-    double *U = nullptr, *V = nullptr, *Vt = nullptr, *Ub = nullptr, *Vb = nullptr, *Gvb = nullptr;
-    double* A = nullptr;
+    double *X = nullptr, *Xt = nullptr;       // samples x genes, and its transposed copy genes x samples
+    double *U = nullptr, *Vbuf[2] = {nullptr, nullptr}, *Ub = nullptr, *Vb = nullptr, *Gvb = nullptr;
+    int vcur = 0;                             // Vbuf[vcur] is the current V
+    double* Apart = nullptr;                  // pass-1 partials [chunks1][m][k]
     double *Gv = nullptr, *Gu_part = nullptr, *Gv_part = nullptr, *VB_part = nullptr;
     double* Bpart = nullptr;
     double* red = nullptr;
@@ -61,6 +59,7 @@ struct prmf_handle {
     int* step_counter = nullptr;
     int obj_capacity = 0;
     int32_t *active = nullptr, *pos = nullptr;
+    double* scores_buf = nullptr;             // 3 x k x P tables of prmf_scores
     bool have_X = false, have_UV = false, have_pw = false, have_active = false, pos_dirty = true;
     std::vector<int32_t> active_host;
 
@@ -72,8 +71,10 @@ struct prmf_handle {
     std::vector<int32_t> support_host;
 
     // launch geometry
-    int xv_grid = 0, uu_grid = 0, uu_rows = 0, vu_grid = 0, vu_rows = 0;
-    int panels = 0, panel_w = 0, chunks = 0;
+    int uu_grid = 0, uu_rows = 0, vu_grid = 0, vu_rows = 0;
+    int panels1 = 0, panel_w1 = 0, chunks1 = 0;      // pass 1: panels over samples, chunks over genes
+    int64_t rows_per_chunk1 = 0;
+    int panels = 0, panel_w = 0, chunks = 0;         // pass 2: panels over genes, chunks over samples
     int64_t rows_per_chunk = 0;
     int ktile = 0, nq = 1;
 
@@ -85,9 +86,9 @@ struct prmf_handle {
     int64_t launches = 0;
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
-    std::vector<std::pair<int, int>> ev_pairs;   // (kind, pool index of start); kind 0 = xv, 1 = xtu
-    double xv_ms = 0, xtu_ms = 0;
-    int64_t xv_n = 0, xtu_n = 0;
+    std::vector<std::pair<int, int>> ev_pairs;   // (phase, pool index of start event; end = start + 1)
+    double phase_ms[PRMF_N_PHASES] = {0, 0, 0, 0, 0, 0};
+    int64_t phase_n[PRMF_N_PHASES] = {0, 0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -152,17 +153,11 @@ int set_smem(prmf_handle* h, F kernel, size_t bytes) {
 }
 
 // ---- templated launch dispatch ---------------------------------------------------------------------
-constexpr int kRW = 4;
-
 template <int KT>
-void launch_xv_t(prmf_handle* h, int k0) {
-    xv_kernel<KT, kRW><<<h->xv_grid, 256, 0, h->stream>>>(h->X, h->ldx, h->m, h->n2, h->Vt, h->ldvt, k0, h->k, h->A);
-}
-template <int KT>
-void launch_xtu_t(prmf_handle* h, int k0) {
-    dim3 grid(h->panels, h->chunks);
-    xtu_kernel<KT><<<grid, 256, 0, h->stream>>>(h->X, h->ldx, h->m, (int)h->n, h->U, h->k, k0, h->panel_w,
-                                                h->rows_per_chunk, h->Bpart);
+void launch_skinny_t(prmf_handle* h, const double* M, int64_t ldm, int64_t rows, int64_t cols, const double* W,
+                     int k0, int panels, int panel_w, int chunks, int64_t rows_per_chunk, double* out) {
+    dim3 grid(panels, chunks);
+    skinny_tn_kernel<KT><<<grid, 256, 0, h->stream>>>(M, ldm, rows, cols, W, h->k, k0, panel_w, rows_per_chunk, out);
 }
 
 #define KT_SWITCH(kt, FN, ...)          \
@@ -179,16 +174,19 @@ void launch_xtu_t(prmf_handle* h, int k0) {
         default: FN<10>(__VA_ARGS__); break; \
     }
 
+// pass 1: A partials = Xt^T . V   (M = Xt: n rows x m cols)
 int launch_xv(prmf_handle* h) {
     if (h->m == 0) return PRMF_OK;
     for (int k0 = 0; k0 < h->k; k0 += h->ktile) {
         int kt = std::min(h->ktile, h->k - k0);
-        KT_SWITCH(kt, launch_xv_t, h, k0);
-        LAUNCH_CHECK("xv_kernel");
+        KT_SWITCH(kt, launch_skinny_t, h, h->Xt, h->ldxt, h->n, h->m, h->Vbuf[h->vcur], k0, h->panels1, h->panel_w1,
+                  h->chunks1, h->rows_per_chunk1, h->Apart);
+        LAUNCH_CHECK("skinny_tn_kernel(pass 1)");
     }
     return PRMF_OK;
 }
 
+// pass 2: B partials = X^T . U_new   (M = X: m rows x n cols)
 int launch_xtu(prmf_handle* h) {
     if (h->m == 0) {
         CU(cudaMemsetAsync(h->Bpart, 0, sizeof(double) * h->chunks * h->n * h->k, h->stream));
@@ -196,8 +194,9 @@ int launch_xtu(prmf_handle* h) {
     }
     for (int k0 = 0; k0 < h->k; k0 += h->ktile) {
         int kt = std::min(h->ktile, h->k - k0);
-        KT_SWITCH(kt, launch_xtu_t, h, k0);
-        LAUNCH_CHECK("xtu_kernel");
+        KT_SWITCH(kt, launch_skinny_t, h, h->X, h->ldx, h->m, h->n, h->U, k0, h->panels, h->panel_w, h->chunks,
+                  h->rows_per_chunk, h->Bpart);
+        LAUNCH_CHECK("skinny_tn_kernel(pass 2)");
     }
     return PRMF_OK;
 }
@@ -213,30 +212,32 @@ int launch_xtu(prmf_handle* h) {
 size_t uu_smem(const prmf_handle* h) { return sizeof(double) * ((size_t)h->k * h->k + (size_t)h->uu_rows * h->k); }
 size_t vu_smem(const prmf_handle* h) { return sizeof(double) * ((size_t)h->k * h->k + (size_t)h->vu_rows * h->k); }
 size_t gram_smem(const prmf_handle* h) { return sizeof(double) * ((size_t)h->vu_rows * h->k); }
-size_t obj_smem(const prmf_handle* h) { return sizeof(double) * ((size_t)h->k * h->k); }
+size_t obj_smem(const prmf_handle* h) { return sizeof(double) * ((size_t)h->k * h->k + 2 * (size_t)h->k); }
 
 int launch_u_update(prmf_handle* h) {
+    if (h->m == 0) {
+        CU(cudaMemsetAsync(h->Gu_part, 0, sizeof(double) * h->uu_grid * h->k * h->k, h->stream));
+        return PRMF_OK;
+    }
     NQ_SWITCH(h->nq, (u_update_kernel<NQ><<<h->uu_grid, 256, uu_smem(h), h->stream>>>(
-                         h->U, h->A, h->Gv, h->m, h->k, h->uu_rows, h->Gu_part)));
+                         h->U, h->Apart, h->chunks1, h->Gv, h->m, h->k, h->uu_rows, h->Gu_part)));
     LAUNCH_CHECK("u_update_kernel");
     return PRMF_OK;
 }
 
 int launch_v_update(prmf_handle* h) {
     NQ_SWITCH(h->nq, (v_update_kernel<NQ><<<h->vu_grid, 256, vu_smem(h), h->stream>>>(
-                         h->V, h->Vt, h->ldvt, h->red, (int)h->n, h->k, h->pw, h->active, h->pos, h->gd,
-                         h->vu_rows, h->Gv_part, h->VB_part)));
+                         h->Vbuf[h->vcur], h->Vbuf[h->vcur ^ 1], h->red, (int)h->n, h->k, h->pw, h->active, h->pos,
+                         h->gd, h->vu_rows, h->Gv_part, h->VB_part)));
     LAUNCH_CHECK("v_update_kernel");
-    const int64_t nk = h->n * h->k;
-    vt_to_v_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, h->stream>>>(h->Vt, h->ldvt, (int)h->n, h->k, h->V);
-    LAUNCH_CHECK("vt_to_v_kernel");
+    h->vcur ^= 1;
     return PRMF_OK;
 }
 
 // Gv = V^T V from scratch (after set_UV / restore)
 int recompute_Gv(prmf_handle* h) {
     NQ_SWITCH(h->nq, (gram_rows_kernel<NQ><<<h->vu_grid, 256, gram_smem(h), h->stream>>>(
-                         h->V, h->n, h->k, h->vu_rows, h->Gv_part)));
+                         h->Vbuf[h->vcur], h->n, h->k, h->vu_rows, h->Gv_part)));
     LAUNCH_CHECK("gram_rows_kernel");
     const int kk2 = h->k * h->k;
     sum_gram_parts_kernel<<<(kk2 + 255) / 256, 256, 0, h->stream>>>(h->Gv_part, h->vu_grid, kk2, h->Gv);
@@ -284,7 +285,8 @@ void harvest_events(prmf_handle* h) {
     for (auto& pr : h->ev_pairs) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, h->ev_pool[pr.second], h->ev_pool[pr.second + 1]) == cudaSuccess) {
-            if (pr.first == 0) { h->xv_ms += ms; h->xv_n++; } else { h->xtu_ms += ms; h->xtu_n++; }
+            h->phase_ms[pr.first] += ms;
+            h->phase_n[pr.first]++;
         }
     }
     for (auto e : h->ev_pool) cudaEventDestroy(e);
@@ -306,27 +308,42 @@ int enqueue_steps(prmf_handle* h, int n_steps, double gamma, double delta, doubl
     const int64_t nk = h->n * h->k;
     const int kk2 = h->k * h->k;
     const size_t red_count = (size_t)nk + kk2 + 2;
-    for (int s = 0; s < n_steps; ++s) {
+    // phase timing (profiling mode only): an event pair around each phase of the step
+    auto tic = [&](int phase) {
+        if (!h->profiling) return;
         int i0 = 0, i1 = 0;
-        if (h->profiling) { cudaEvent_t e0 = get_event(h, &i0); get_event(h, &i1); cudaEventRecord(e0, h->stream); }
-        if ((rc = launch_xv(h))) return rc;
-        if (h->profiling) { cudaEventRecord(h->ev_pool[i0 + 1], h->stream); h->ev_pairs.push_back({0, i0}); }
-        if ((rc = launch_u_update(h))) return rc;
-        if (h->profiling) { cudaEvent_t e0 = get_event(h, &i0); get_event(h, &i1); cudaEventRecord(e0, h->stream); }
-        if ((rc = launch_xtu(h))) return rc;
-        if (h->profiling) { cudaEventRecord(h->ev_pool[i0 + 1], h->stream); h->ev_pairs.push_back({1, i0}); }
-        reduce_pack_kernel<<<(unsigned)((nk + kk2 + 255) / 256), 256, 0, h->stream>>>(
+        cudaEvent_t e0 = get_event(h, &i0);
+        get_event(h, &i1);
+        cudaEventRecord(e0, h->stream);
+        h->ev_pairs.push_back({phase, i0});
+    };
+    auto toc = [&]() {
+        if (!h->profiling) return;
+        cudaEventRecord(h->ev_pool[h->ev_pairs.back().second + 1], h->stream);
+    };
+    for (int s = 0; s < n_steps; ++s) {
+        tic(0); rc = launch_xv(h); toc();
+        if (rc) return rc;
+        tic(1); rc = launch_u_update(h); toc();
+        if (rc) return rc;
+        tic(2); rc = launch_xtu(h); toc();
+        if (rc) return rc;
+        tic(3);
+        reduce_pack_kernel<<<(unsigned)((nk + kk2 + 2 + 255) / 256), 256, 0, h->stream>>>(
             h->Bpart, h->chunks, nk, h->Gu_part, h->uu_grid, h->k, h->red);
         LAUNCH_CHECK("reduce_pack_kernel");
-        if ((rc = allreduce(h, h->red, red_count))) return rc;
-        fro_from_gram_kernel<<<1, 32, 0, h->stream>>>(h->red, nk, h->k);
-        LAUNCH_CHECK("fro_from_gram_kernel");
-        if ((rc = launch_v_update(h))) return rc;
-        objective_kernel<<<1, 1024, obj_smem(h), h->stream>>>(h->V, (int)h->n, h->k, h->red, h->Gv_part, h->VB_part,
-                                                              h->vu_grid, h->normX_sq, h->pw, h->active, h->Gv,
-                                                              h->gd, tradeoff, h->obj, h->step_counter,
+        rc = allreduce(h, h->red, red_count);
+        toc();
+        if (rc) return rc;
+        tic(4); rc = launch_v_update(h); toc();
+        if (rc) return rc;
+        tic(5);
+        objective_kernel<<<1, 1024, obj_smem(h), h->stream>>>(h->Vbuf[h->vcur], (int)h->n, h->k, h->red, h->Gv_part,
+                                                              h->VB_part, h->vu_grid, h->normX_sq, h->pw, h->active,
+                                                              h->Gv, h->gd, tradeoff, h->obj, h->step_counter,
                                                               h->obj_capacity);
         LAUNCH_CHECK("objective_kernel");
+        toc();
     }
     return PRMF_OK;
 }
@@ -344,9 +361,12 @@ int collect(prmf_handle* h, int n_steps, double* obj_parts, double* gamma_delta_
 }
 
 int finish_X(prmf_handle* h) {
-    // ||X||^2 partial of this rank, all-reduced once
+    // transposed copy for pass 1, then ||X||^2 partial of this rank, all-reduced once
     const int blocks = h->sm_count * 4;
     if (h->m > 0) {
+        dim3 tg((unsigned)((h->n + 31) / 32), (unsigned)((h->m + 31) / 32));
+        transpose_kernel<<<tg, 256, 0, h->stream>>>(h->X, h->ldx, h->m, h->n, h->Xt, h->ldxt);
+        LAUNCH_CHECK("transpose_kernel");
         sumsq_kernel<<<blocks, 256, 0, h->stream>>>(h->X, h->ldx, h->m, h->n2, h->scal_part);
         LAUNCH_CHECK("sumsq_kernel");
         sum_partials_kernel<<<1, 256, 0, h->stream>>>(h->scal_part, blocks, h->normX_sq);
@@ -399,7 +419,7 @@ int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global
     h->sm_count = prop.multiProcessorCount;
     h->m = m_local; h->m_global = m_global; h->n = n; h->k = k;
     h->ldx = round_up(n, 16);        // rows start on 128-byte lines; pad columns are zero
-    h->ldvt = round_up(n, 16);
+    h->ldxt = round_up(std::max<int64_t>(1, m_local), 16);
     h->n2 = (int)round_up(n, 2);
     if (stream) { h->stream = (cudaStream_t)stream; }
     else {
@@ -410,26 +430,33 @@ int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global
     // launch geometry
     h->ktile = pick_ktile(k);
     h->nq = pick_nq(k);
-    h->xv_grid = h->sm_count * 2;
     h->uu_rows = (int)std::max<int64_t>(8, std::min<int64_t>(128, 4096 / k));
     h->uu_grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count * 2, (m_local + h->uu_rows - 1) / h->uu_rows));
     h->vu_rows = (int)std::max<int64_t>(8, std::min<int64_t>(32, 4096 / k));
     h->vu_grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count * 2, (n + h->vu_rows - 1) / h->vu_rows));
+    // pass 2 (X^T.U): column panels over genes, row chunks over samples
     h->panels = (int)((n + 1023) / 1024);
     h->panel_w = (int)round_up((n + h->panels - 1) / h->panels, 4);
     h->chunks = std::max(1, (h->sm_count * 2) / h->panels);
-    if (m_local > 0) h->chunks = (int)std::min<int64_t>(h->chunks, std::max<int64_t>(1, m_local / 8));
+    if (m_local > 0) h->chunks = (int)std::min<int64_t>(h->chunks, std::max<int64_t>(1, m_local / 64));
     h->rows_per_chunk = std::max<int64_t>(1, (m_local + h->chunks - 1) / h->chunks);
+    // pass 1 (Xt^T.V): column panels over samples, row chunks over genes
+    h->panels1 = (int)std::max<int64_t>(1, (m_local + 1023) / 1024);
+    h->panel_w1 = (int)round_up((std::max<int64_t>(1, m_local) + h->panels1 - 1) / h->panels1, 4);
+    h->chunks1 = std::max(1, (h->sm_count * 2) / h->panels1);
+    h->chunks1 = (int)std::min<int64_t>(h->chunks1, std::max<int64_t>(1, n / 64));
+    h->rows_per_chunk1 = std::max<int64_t>(1, (n + h->chunks1 - 1) / h->chunks1);
 
     int rc = 0;
     const int64_t nk = n * k;
     const int kk2 = k * k;
 #define ALLOC(ptr, count) if (!rc) rc = dalloc(h, &ptr, (size_t)(count))
     ALLOC(h->X, (size_t)std::max<int64_t>(1, m_local) * h->ldx);
+    ALLOC(h->Xt, (size_t)n * h->ldxt);
     ALLOC(h->U, std::max<int64_t>(1, m_local) * k);
     ALLOC(h->Ub, std::max<int64_t>(1, m_local) * k);
-    ALLOC(h->A, std::max<int64_t>(1, m_local) * k);
-    ALLOC(h->V, nk); ALLOC(h->Vb, nk); ALLOC(h->Vt, (size_t)k * h->ldvt);
+    ALLOC(h->Apart, (size_t)h->chunks1 * std::max<int64_t>(1, m_local) * k);
+    ALLOC(h->Vbuf[0], nk); ALLOC(h->Vbuf[1], nk); ALLOC(h->Vb, nk);
     ALLOC(h->Gv, kk2); ALLOC(h->Gvb, kk2);
     ALLOC(h->Gu_part, (size_t)h->uu_grid * kk2);
     ALLOC(h->Gv_part, (size_t)h->vu_grid * kk2);
@@ -444,7 +471,7 @@ int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global
     ALLOC(h->pos, nk);
 #undef ALLOC
     if (!rc) {
-        cudaMemsetAsync(h->Vt, 0, sizeof(double) * k * h->ldvt, h->stream);
+        cudaMemsetAsync(h->Xt, 0, sizeof(double) * n * h->ldxt, h->stream);
         cudaMemsetAsync(h->red, 0, sizeof(double) * (nk + kk2 + 2), h->stream);
         cudaMemsetAsync(h->Gu_part, 0, sizeof(double) * h->uu_grid * kk2, h->stream);
         e = cudaStreamSynchronize(h->stream);
@@ -474,9 +501,9 @@ int prmf_destroy(prmf_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     harvest_events(h);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-    void* bufs[] = {h->own_X ? h->X : nullptr, h->U, h->V, h->Vt, h->Ub, h->Vb, h->Gvb, h->A, h->Gv, h->Gu_part,
+    void* bufs[] = {h->X, h->Xt, h->U, h->Vbuf[0], h->Vbuf[1], h->Ub, h->Vb, h->Gvb, h->Apart, h->Gv, h->Gu_part,
                     h->Gv_part, h->VB_part, h->Bpart, h->red, h->normX_sq, h->scal_part, h->gd, h->obj,
-                    h->step_counter, h->active, h->pos};
+                    h->step_counter, h->active, h->pos, h->scores_buf};
     for (void* b : bufs) if (b) cudaFree(b);
     for (void* b : h->pw_allocs) cudaFree(b);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -576,6 +603,9 @@ int prmf_set_pathways(prmf_handle* h, int32_t P, const int64_t* path_ptr, const 
     if (!rc) rc = up(isd.data(), sizeof(double) * S, (const void**)&pw.isd);
     if (rc) return rc;
     CU(cudaStreamSynchronize(h->stream));
+    if (h->scores_buf) cudaFree(h->scores_buf);
+    h->scores_buf = nullptr;
+    if ((rc = dalloc(h, &h->scores_buf, (size_t)3 * h->k * P))) return rc;
     h->pw = pw; h->S = S; h->E = E;
     h->path_ptr_host.assign(path_ptr, path_ptr + P + 1);
     h->have_pw = true;
@@ -591,9 +621,7 @@ int prmf_set_UV(prmf_handle* h, const double* U_local, const double* V) {
         CU(cudaMemcpyAsync(h->U, U_local, sizeof(double) * h->m * h->k, cudaMemcpyHostToDevice, h->stream));
     if (V) {
         const int64_t nk = h->n * h->k;
-        CU(cudaMemcpyAsync(h->V, V, sizeof(double) * nk, cudaMemcpyHostToDevice, h->stream));
-        v_to_vt_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, h->stream>>>(h->V, (int)h->n, h->k, h->Vt, h->ldvt);
-        LAUNCH_CHECK("v_to_vt_kernel");
+        CU(cudaMemcpyAsync(h->Vbuf[h->vcur], V, sizeof(double) * nk, cudaMemcpyHostToDevice, h->stream));
         int rc = recompute_Gv(h);
         if (rc) return rc;
     }
@@ -607,7 +635,7 @@ int prmf_get_UV(prmf_handle* h, double* U_local, double* V) {
     CU(cudaSetDevice(h->device));
     if (U_local && h->m > 0)
         CU(cudaMemcpyAsync(U_local, h->U, sizeof(double) * h->m * h->k, cudaMemcpyDeviceToHost, h->stream));
-    if (V) CU(cudaMemcpyAsync(V, h->V, sizeof(double) * h->n * h->k, cudaMemcpyDeviceToHost, h->stream));
+    if (V) CU(cudaMemcpyAsync(V, h->Vbuf[h->vcur], sizeof(double) * h->n * h->k, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return PRMF_OK;
 }
@@ -649,18 +677,14 @@ int prmf_scores(prmf_handle* h, double* mass, double* quad_norm, double* quad_ra
     if (!h->have_pw || !h->have_UV) return fail(h, PRMF_ERR_STATE, "prmf_scores needs pathways and V");
     CU(cudaSetDevice(h->device));
     const size_t cnt = (size_t)h->k * h->pw.P;
-    double* d = nullptr;
-    int rc = dalloc(h, &d, cnt * 3);
-    if (rc) return rc;
-    scores_kernel<<<std::min(h->pw.P, h->sm_count * 8), 256, 0, h->stream>>>(h->V, h->k, h->Gv, h->pw, d, d + cnt, d + 2 * cnt);
-    h->launches++;
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess && mass) e = cudaMemcpyAsync(mass, d, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess && quad_norm) e = cudaMemcpyAsync(quad_norm, d + cnt, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess && quad_raw) e = cudaMemcpyAsync(quad_raw, d + 2 * cnt, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(d);
-    if (e != cudaSuccess) return fail(h, PRMF_ERR_CUDA, "prmf_scores: %s", cudaGetErrorString(e));
+    double* d = h->scores_buf;
+    scores_kernel<<<std::min(h->pw.P, h->sm_count * 8), 256, 0, h->stream>>>(h->Vbuf[h->vcur], h->k, h->Gv, h->pw, d,
+                                                                             d + cnt, d + 2 * cnt);
+    LAUNCH_CHECK("scores_kernel");
+    if (mass) CU(cudaMemcpyAsync(mass, d, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (quad_norm) CU(cudaMemcpyAsync(quad_norm, d + cnt, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (quad_raw) CU(cudaMemcpyAsync(quad_raw, d + 2 * cnt, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return PRMF_OK;
 }
 
@@ -668,7 +692,7 @@ int prmf_snapshot_best(prmf_handle* h) {
     if (!h) return PRMF_ERR_ARG;
     CU(cudaSetDevice(h->device));
     if (h->m > 0) CU(cudaMemcpyAsync(h->Ub, h->U, sizeof(double) * h->m * h->k, cudaMemcpyDeviceToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->Vb, h->V, sizeof(double) * h->n * h->k, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->Vb, h->Vbuf[h->vcur], sizeof(double) * h->n * h->k, cudaMemcpyDeviceToDevice, h->stream));
     CU(cudaMemcpyAsync(h->Gvb, h->Gv, sizeof(double) * h->k * h->k, cudaMemcpyDeviceToDevice, h->stream));
     return PRMF_OK;
 }
@@ -678,10 +702,8 @@ int prmf_restore_best(prmf_handle* h) {
     CU(cudaSetDevice(h->device));
     if (h->m > 0) CU(cudaMemcpyAsync(h->U, h->Ub, sizeof(double) * h->m * h->k, cudaMemcpyDeviceToDevice, h->stream));
     const int64_t nk = h->n * h->k;
-    CU(cudaMemcpyAsync(h->V, h->Vb, sizeof(double) * nk, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->Vbuf[h->vcur], h->Vb, sizeof(double) * nk, cudaMemcpyDeviceToDevice, h->stream));
     CU(cudaMemcpyAsync(h->Gv, h->Gvb, sizeof(double) * h->k * h->k, cudaMemcpyDeviceToDevice, h->stream));
-    v_to_vt_kernel<<<(unsigned)((nk + 255) / 256), 256, 0, h->stream>>>(h->V, (int)h->n, h->k, h->Vt, h->ldvt);
-    LAUNCH_CHECK("v_to_vt_kernel");
     CU(cudaStreamSynchronize(h->stream));
     return PRMF_OK;
 }
@@ -695,7 +717,7 @@ int prmf_residual_sq(prmf_handle* h, double* out) {
     int rc = dalloc(h, &d, 1);
     if (rc) return rc;
     if (h->m > 0) {
-        residual_kernel<<<blocks, 256, 0, h->stream>>>(h->X, h->ldx, h->m, (int)h->n, h->U, h->V, h->k, h->scal_part);
+        residual_kernel<<<blocks, 256, 0, h->stream>>>(h->X, h->ldx, h->m, (int)h->n, h->U, h->Vbuf[h->vcur], h->k, h->scal_part);
         h->launches++;
         sum_partials_kernel<<<1, 256, 0, h->stream>>>(h->scal_part, blocks, d);
         h->launches++;
@@ -752,12 +774,13 @@ int prmf_set_profiling(prmf_handle* h, int on) {
     return PRMF_OK;
 }
 
-int prmf_kernel_times(prmf_handle* h, int reset, double* xv_ms, double* xtu_ms, int64_t* launches) {
+int prmf_kernel_times(prmf_handle* h, int reset, double* phase_ms, int64_t* phase_count) {
     if (!h) return PRMF_ERR_ARG;
-    if (xv_ms) *xv_ms = h->xv_ms;
-    if (xtu_ms) *xtu_ms = h->xtu_ms;
-    if (launches) { launches[0] = h->xv_n; launches[1] = h->xtu_n; }
-    if (reset) { h->xv_ms = h->xtu_ms = 0; h->xv_n = h->xtu_n = 0; }
+    for (int i = 0; i < PRMF_N_PHASES; ++i) {
+        if (phase_ms) phase_ms[i] = h->phase_ms[i];
+        if (phase_count) phase_count[i] = h->phase_n[i];
+        if (reset) { h->phase_ms[i] = 0; h->phase_n[i] = 0; }
+    }
     return PRMF_OK;
 }
 

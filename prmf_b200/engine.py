@@ -166,10 +166,11 @@ class CudaEngine:
         self._ck(self.lib.prmf_set_profiling(self.h, 1 if on else 0))
 
     def kernel_times(self, reset=True):
-        a, b = ctypes.c_double(), ctypes.c_double()
-        n = (ctypes.c_int64 * 2)()
-        self._ck(self.lib.prmf_kernel_times(self.h, 1 if reset else 0, ctypes.byref(a), ctypes.byref(b), n))
-        return {"xv_ms": a.value, "xtu_ms": b.value, "xv_launches": int(n[0]), "xtu_launches": int(n[1])}
+        """{phase: (total_ms, count)} for the phases of the inner step timed in profiling mode."""
+        ms = (ctypes.c_double * _lib.N_PHASES)()
+        n = (ctypes.c_int64 * _lib.N_PHASES)()
+        self._ck(self.lib.prmf_kernel_times(self.h, 1 if reset else 0, ms, n))
+        return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(_lib.PHASES)}
 
     @property
     def stream(self):

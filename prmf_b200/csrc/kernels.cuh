@@ -18,6 +18,49 @@ __device__ __forceinline__ double2 ld_stream(const double* p) {
     return r;
 }
 
+// ---- sm_100a async-copy primitives (TMA bulk copies completed on mbarriers) ------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared (TMA engine, SASS UBLKCP); dst/src 16-byte aligned, bytes % 16 == 0
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+            "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -224,6 +267,139 @@ skinny_tn_kernel(const double* __restrict__ M, int64_t ldm, int64_t rows_total, 
 #pragma unroll
                 for (int c = 0; c < KT; ++c) out[c] = acc[g][c];
             }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// TMA version of the X-stream kernel (single factor tile, KT == k).  Same math and same output layout as
+// skinny_tn_kernel; the difference is how bytes move: a producer warp issues 1-D bulk async copies
+// (cp.async.bulk, SASS UBLKCP) of RS row pieces of M (<= 8 KB each, contiguous) plus the RS matching rows
+// of W per stage into a ring of `stages` shared-memory buffers; completion is tracked with mbarrier
+// transaction counts, and the 8 consumer warps release a buffer through an "empty" mbarrier.  Bytes in
+// flight per SM are set by the ring (>= 100 KB), not by registers, which is what the LDG version lacked
+// (ncu: long_scoreboard stalls, 24 % warps active, 84 % of the measured copy bandwidth).
+// Thread t owns the double2 columns t and t + H of the panel (H = panel_w / 4), so shared-memory reads of a
+// warp are contiguous 512-byte runs (conflict free); W rows are broadcast reads.
+// W must be readable for RS rows past the last row of the chunk (the host pads U and V allocations).
+// ----------------------------------------------------------------------------------------------------
+constexpr int kTmaConsumerWarps = 8;
+constexpr int kTmaThreads = (kTmaConsumerWarps + 1) * 32;
+
+template <int KT, int RS>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+skinny_tma_kernel(const double* __restrict__ M, int64_t ldm, int64_t rows_total, int64_t cols,
+                  const double* __restrict__ W, int panel_w, int64_t rows_per_chunk, int stages,
+                  double* __restrict__ OutPart) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int panel = blockIdx.x;
+    const int64_t chunk = blockIdx.y;
+    const int64_t c0 = (int64_t)panel * panel_w;                          // first column of the panel
+    const int width = (int)min((int64_t)panel_w, ldm - c0);               // columns held (multiple of 4)
+    const uint32_t row_bytes = (uint32_t)width * 8u;
+    const uint32_t x_stage_bytes = (uint32_t)RS * (uint32_t)panel_w * 8u;
+    const uint32_t w_bytes = (uint32_t)RS * KT * 8u;
+    const uint32_t stage_bytes = x_stage_bytes + ((w_bytes + 127u) & ~127u);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + stages;
+    const int64_t rbeg = chunk * rows_per_chunk;
+    const int64_t rend = min(rows_total, rbeg + rows_per_chunk);
+    const int nstage_iters = rend > rbeg ? (int)((rend - rbeg + RS - 1) / RS) : 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s2 = 0; s2 < stages; ++s2) {
+            mbar_init(&full_bar[s2], 1);
+            mbar_init(&empty_bar[s2], kTmaConsumerWarps);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == kTmaConsumerWarps) {
+        // ===== producer warp: lanes 0..RS-1 copy one row piece each, lane 0 also copies the W rows =====
+        const uint64_t pol_x = l2_policy_evict_first();
+        const uint64_t pol_w = l2_policy_evict_last();
+        int s2 = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < nstage_iters; ++it) {
+            const int64_t r0 = rbeg + (int64_t)it * RS;
+            const int rows = (int)min((int64_t)RS, rend - r0);
+            if (lane == 0) mbar_wait(&empty_bar[s2], phase ^ 1u);
+            __syncwarp();
+            unsigned char* sx = smem_raw + (size_t)s2 * stage_bytes;
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&full_bar[s2], (uint32_t)rows * row_bytes + w_bytes);
+                bulk_g2s(sx + x_stage_bytes, W + r0 * KT, w_bytes, &full_bar[s2], pol_w);
+            }
+            __syncwarp();
+            if (lane < rows)
+                bulk_g2s(sx + (size_t)lane * panel_w * 8, M + (r0 + lane) * ldm + c0, row_bytes, &full_bar[s2], pol_x);
+            if (++s2 == stages) { s2 = 0; phase ^= 1u; }
+        }
+        return;
+    }
+
+    // ===== consumer warps =====
+    const int H = panel_w >> 2;                        // double2 columns per half panel
+    const int t = threadIdx.x;                         // 0..255
+    const bool active = t < H && (2 * t) < width;      // first pair inside the held columns
+    const bool active2 = t < H && (2 * (t + H)) < width;
+    double acc[4][KT];
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int c = 0; c < KT; ++c) acc[g][c] = 0.0;
+    int s2 = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < nstage_iters; ++it) {
+        const int rows = (int)min((int64_t)RS, rend - (rbeg + (int64_t)it * RS));
+        mbar_wait(&full_bar[s2], phase);
+        const unsigned char* sx = smem_raw + (size_t)s2 * stage_bytes;
+        const double* sw = reinterpret_cast<const double*>(sx + x_stage_bytes);
+        if (rows == RS) {
+#pragma unroll
+            for (int r = 0; r < RS; ++r) {
+                const double2* xrow = reinterpret_cast<const double2*>(sx + (size_t)r * panel_w * 8);
+                const double2 xa = active ? xrow[t] : make_double2(0.0, 0.0);
+                const double2 xb = active2 ? xrow[t + H] : make_double2(0.0, 0.0);
+#pragma unroll
+                for (int c = 0; c < KT; ++c) {
+                    const double u = sw[r * KT + c];
+                    acc[0][c] = fma(xa.x, u, acc[0][c]);
+                    acc[1][c] = fma(xa.y, u, acc[1][c]);
+                    acc[2][c] = fma(xb.x, u, acc[2][c]);
+                    acc[3][c] = fma(xb.y, u, acc[3][c]);
+                }
+            }
+        } else {
+            for (int r = 0; r < rows; ++r) {
+                const double2* xrow = reinterpret_cast<const double2*>(sx + (size_t)r * panel_w * 8);
+                const double2 xa = active ? xrow[t] : make_double2(0.0, 0.0);
+                const double2 xb = active2 ? xrow[t + H] : make_double2(0.0, 0.0);
+#pragma unroll
+                for (int c = 0; c < KT; ++c) {
+                    const double u = sw[r * KT + c];
+                    acc[0][c] = fma(xa.x, u, acc[0][c]);
+                    acc[1][c] = fma(xa.y, u, acc[1][c]);
+                    acc[2][c] = fma(xb.x, u, acc[2][c]);
+                    acc[3][c] = fma(xb.y, u, acc[3][c]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s2]);
+        if (++s2 == stages) { s2 = 0; phase ^= 1u; }
+    }
+    // columns owned: c0 + 2t, c0 + 2t + 1, c0 + 2(t+H), c0 + 2(t+H) + 1
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int64_t j = c0 + 2 * (int64_t)(g < 2 ? t : t + H) + (g & 1);
+        const bool ok = (g < 2 ? active : active2) && j < cols;
+        if (ok) {
+            double* out = OutPart + ((int64_t)chunk * cols + j) * KT;
+#pragma unroll
+            for (int c = 0; c < KT; ++c) out[c] = acc[g][c];
         }
     }
 }

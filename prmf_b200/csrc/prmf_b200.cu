@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -77,6 +78,12 @@ struct prmf_handle {
     int panels = 0, panel_w = 0, chunks = 0;         // pass 2: panels over genes, chunks over samples
     int64_t rows_per_chunk = 0;
     int ktile = 0, nq = 1;
+    // TMA (bulk-async) variant of the X-stream kernel: used when one factor tile covers k
+    bool use_tma = false;
+    int tma_rs = 8, tma_stages = 3;
+    int tpanels1 = 0, tpanel_w1 = 0, tchunks1 = 0, tpanels = 0, tpanel_w = 0, tchunks = 0;
+    int64_t trows_per_chunk1 = 0, trows_per_chunk = 0;
+    size_t tma_smem1 = 0, tma_smem2 = 0;
 
     // multi-GPU
     NcclComm comm = nullptr;
@@ -174,9 +181,47 @@ void launch_skinny_t(prmf_handle* h, const double* M, int64_t ldm, int64_t rows,
         default: FN<10>(__VA_ARGS__); break; \
     }
 
+template <int KT>
+int launch_skinny_tma_t(prmf_handle* h, const double* M, int64_t ldm, int64_t rows, int64_t cols, const double* W,
+                        int panels, int panel_w, int chunks, int64_t rows_per_chunk, size_t smem, double* out) {
+    dim3 grid(panels, chunks);
+    if (h->tma_rs == 4) {
+        CU(cudaFuncSetAttribute(skinny_tma_kernel<KT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        skinny_tma_kernel<KT, 4><<<grid, kTmaThreads, smem, h->stream>>>(M, ldm, rows, cols, W, panel_w, rows_per_chunk,
+                                                                         h->tma_stages, out);
+    } else {
+        CU(cudaFuncSetAttribute(skinny_tma_kernel<KT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        skinny_tma_kernel<KT, 8><<<grid, kTmaThreads, smem, h->stream>>>(M, ldm, rows, cols, W, panel_w, rows_per_chunk,
+                                                                         h->tma_stages, out);
+    }
+    return PRMF_OK;
+}
+
+#define KT_SWITCH_RC(kt, rc, FN, ...)          \
+    switch (kt) {                              \
+        case 1: rc = FN<1>(__VA_ARGS__); break;   \
+        case 2: rc = FN<2>(__VA_ARGS__); break;   \
+        case 3: rc = FN<3>(__VA_ARGS__); break;   \
+        case 4: rc = FN<4>(__VA_ARGS__); break;   \
+        case 5: rc = FN<5>(__VA_ARGS__); break;   \
+        case 6: rc = FN<6>(__VA_ARGS__); break;   \
+        case 7: rc = FN<7>(__VA_ARGS__); break;   \
+        case 8: rc = FN<8>(__VA_ARGS__); break;   \
+        case 9: rc = FN<9>(__VA_ARGS__); break;   \
+        default: rc = FN<10>(__VA_ARGS__); break; \
+    }
+
 // pass 1: A partials = Xt^T . V   (M = Xt: n rows x m cols)
 int launch_xv(prmf_handle* h) {
     if (h->m == 0) return PRMF_OK;
+    if (h->use_tma) {
+        int rc = 0;
+        KT_SWITCH_RC(h->k, rc, launch_skinny_tma_t, h, h->Xt, h->ldxt, h->n, h->m, h->Vbuf[h->vcur], h->tpanels1,
+                     h->tpanel_w1, h->tchunks1, h->trows_per_chunk1, h->tma_smem1, h->Apart);
+        if (rc) return rc;
+        LAUNCH_CHECK("skinny_tma_kernel(pass 1)");
+        return PRMF_OK;
+    }
     for (int k0 = 0; k0 < h->k; k0 += h->ktile) {
         int kt = std::min(h->ktile, h->k - k0);
         KT_SWITCH(kt, launch_skinny_t, h, h->Xt, h->ldxt, h->n, h->m, h->Vbuf[h->vcur], k0, h->panels1, h->panel_w1,
@@ -189,7 +234,15 @@ int launch_xv(prmf_handle* h) {
 // pass 2: B partials = X^T . U_new   (M = X: m rows x n cols)
 int launch_xtu(prmf_handle* h) {
     if (h->m == 0) {
-        CU(cudaMemsetAsync(h->Bpart, 0, sizeof(double) * h->chunks * h->n * h->k, h->stream));
+        CU(cudaMemsetAsync(h->Bpart, 0, sizeof(double) * std::max(h->chunks, h->tchunks) * h->n * h->k, h->stream));
+        return PRMF_OK;
+    }
+    if (h->use_tma) {
+        int rc = 0;
+        KT_SWITCH_RC(h->k, rc, launch_skinny_tma_t, h, h->X, h->ldx, h->m, h->n, h->U, h->tpanels, h->tpanel_w,
+                     h->tchunks, h->trows_per_chunk, h->tma_smem2, h->Bpart);
+        if (rc) return rc;
+        LAUNCH_CHECK("skinny_tma_kernel(pass 2)");
         return PRMF_OK;
     }
     for (int k0 = 0; k0 < h->k; k0 += h->ktile) {
@@ -220,7 +273,7 @@ int launch_u_update(prmf_handle* h) {
         return PRMF_OK;
     }
     NQ_SWITCH(h->nq, (u_update_kernel<NQ><<<h->uu_grid, 256, uu_smem(h), h->stream>>>(
-                         h->U, h->Apart, h->chunks1, h->Gv, h->m, h->k, h->uu_rows, h->Gu_part)));
+                         h->U, h->Apart, h->use_tma ? h->tchunks1 : h->chunks1, h->Gv, h->m, h->k, h->uu_rows, h->Gu_part)));
     LAUNCH_CHECK("u_update_kernel");
     return PRMF_OK;
 }
@@ -330,7 +383,7 @@ int enqueue_steps(prmf_handle* h, int n_steps, double gamma, double delta, doubl
         if (rc) return rc;
         tic(3);
         reduce_pack_kernel<<<(unsigned)((nk + kk2 + 2 + 255) / 256), 256, 0, h->stream>>>(
-            h->Bpart, h->chunks, nk, h->Gu_part, h->uu_grid, h->k, h->red);
+            h->Bpart, h->use_tma ? h->tchunks : h->chunks, nk, h->Gu_part, h->uu_grid, h->k, h->red);
         LAUNCH_CHECK("reduce_pack_kernel");
         rc = allreduce(h, h->red, red_count);
         toc();
@@ -447,21 +500,44 @@ int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global
     h->chunks1 = (int)std::min<int64_t>(h->chunks1, std::max<int64_t>(1, n / 64));
     h->rows_per_chunk1 = std::max<int64_t>(1, (n + h->chunks1 - 1) / h->chunks1);
 
+    // TMA variant: one CTA per SM, <= 1024-column panels, row chunks a multiple of the stage height
+    {
+        const char* e1 = getenv("PRMF_TMA");
+        const char* e2 = getenv("PRMF_TMA_RS");
+        const char* e3 = getenv("PRMF_TMA_STAGES");
+        h->use_tma = (k <= 10) && !(e1 && atoi(e1) == 0);
+        if (e2 && atoi(e2) == 4) h->tma_rs = 4;
+        if (e3 && atoi(e3) >= 2 && atoi(e3) <= 12) h->tma_stages = atoi(e3);
+        auto plan = [&](int64_t cols, int64_t rows, int* panels, int* panel_w, int* chunks, int64_t* rpc, size_t* smem) {
+            *panels = (int)std::max<int64_t>(1, (cols + 1023) / 1024);
+            *panel_w = (int)round_up((std::max<int64_t>(1, cols) + *panels - 1) / *panels, 4);
+            *chunks = std::max(1, h->sm_count / *panels);
+            *chunks = (int)std::min<int64_t>(*chunks, std::max<int64_t>(1, rows / (4 * h->tma_rs)));
+            *rpc = round_up(std::max<int64_t>(1, (rows + *chunks - 1) / *chunks), h->tma_rs);
+            const size_t xb = (size_t)h->tma_rs * *panel_w * 8, wb = ((size_t)h->tma_rs * k * 8 + 127) & ~(size_t)127;
+            *smem = h->tma_stages * (xb + wb) + 2 * h->tma_stages * sizeof(uint64_t);
+        };
+        plan(m_local, n, &h->tpanels1, &h->tpanel_w1, &h->tchunks1, &h->trows_per_chunk1, &h->tma_smem1);
+        plan(n, m_local, &h->tpanels, &h->tpanel_w, &h->tchunks, &h->trows_per_chunk, &h->tma_smem2);
+        if (h->tma_smem1 > 220 * 1024 || h->tma_smem2 > 220 * 1024) h->use_tma = false;
+    }
+
     int rc = 0;
     const int64_t nk = n * k;
     const int kk2 = k * k;
+    const int64_t pad_rows = 16;      // bulk copies of W read up to one stage past the last row
 #define ALLOC(ptr, count) if (!rc) rc = dalloc(h, &ptr, (size_t)(count))
     ALLOC(h->X, (size_t)std::max<int64_t>(1, m_local) * h->ldx);
     ALLOC(h->Xt, (size_t)n * h->ldxt);
-    ALLOC(h->U, std::max<int64_t>(1, m_local) * k);
-    ALLOC(h->Ub, std::max<int64_t>(1, m_local) * k);
-    ALLOC(h->Apart, (size_t)h->chunks1 * std::max<int64_t>(1, m_local) * k);
-    ALLOC(h->Vbuf[0], nk); ALLOC(h->Vbuf[1], nk); ALLOC(h->Vb, nk);
+    ALLOC(h->U, (m_local + pad_rows) * k);
+    ALLOC(h->Ub, (m_local + pad_rows) * k);
+    ALLOC(h->Apart, (size_t)std::max(h->chunks1, h->tchunks1) * std::max<int64_t>(1, m_local) * k);
+    ALLOC(h->Vbuf[0], (n + pad_rows) * k); ALLOC(h->Vbuf[1], (n + pad_rows) * k); ALLOC(h->Vb, nk);
     ALLOC(h->Gv, kk2); ALLOC(h->Gvb, kk2);
     ALLOC(h->Gu_part, (size_t)h->uu_grid * kk2);
     ALLOC(h->Gv_part, (size_t)h->vu_grid * kk2);
     ALLOC(h->VB_part, h->vu_grid);
-    ALLOC(h->Bpart, (size_t)h->chunks * nk);
+    ALLOC(h->Bpart, (size_t)std::max(h->chunks, h->tchunks) * nk);
     ALLOC(h->red, (size_t)nk + kk2 + 2);
     ALLOC(h->normX_sq, 1);
     ALLOC(h->scal_part, (size_t)h->sm_count * 8);
@@ -472,6 +548,9 @@ int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global
 #undef ALLOC
     if (!rc) {
         cudaMemsetAsync(h->Xt, 0, sizeof(double) * n * h->ldxt, h->stream);
+        cudaMemsetAsync(h->U, 0, sizeof(double) * (m_local + pad_rows) * k, h->stream);
+        cudaMemsetAsync(h->Vbuf[0], 0, sizeof(double) * (n + pad_rows) * k, h->stream);
+        cudaMemsetAsync(h->Vbuf[1], 0, sizeof(double) * (n + pad_rows) * k, h->stream);
         cudaMemsetAsync(h->red, 0, sizeof(double) * (nk + kk2 + 2), h->stream);
         cudaMemsetAsync(h->Gu_part, 0, sizeof(double) * h->uu_grid * kk2, h->stream);
         e = cudaStreamSynchronize(h->stream);

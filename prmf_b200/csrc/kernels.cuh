@@ -457,13 +457,49 @@ struct Pathways {
     const double* isd;           // S   diag(L)^-1/2, 0 where diag(L) == 0        (:58-62)
 };
 
-// pos[j*k + c] = packed row of gene j in the active pathway of factor c, or -1
-__global__ void build_pos_kernel(Pathways pw, const int32_t* __restrict__ active, int k, int32_t* __restrict__ pos) {
+// Normalised Laplacians of the k ACTIVE pathways, flattened for the objective (:344-352): one diagonal
+// entry per support row and one off-diagonal entry per stored edge, with global gene indices, so the
+// objective needs a single gather of V per entry instead of walking the packed CSR.
+struct ActiveSet {
+    int64_t n_diag, n_off;
+    const int32_t* diag_gene;    // gene of the support row
+    const int32_t* diag_factor;
+    const double* diag_coef;     // isd_r * diag(L)_r * isd_r
+    const int32_t* off_r;        // gene of the row
+    const int32_t* off_c;        // gene of the neighbour
+    const int32_t* off_factor;
+    const double* off_coef;      // isd_r * (-w_rc * isd_c)   (0 for a self loop: it is part of diag(L))
+};
+
+// pos[j*k + c] = packed row of gene j in the active pathway of factor c (or -1, preset by a memset), and
+// the flattened ActiveSet.  grid = (blocks, k); doff/eoff = per-factor offsets into the flat arrays.
+__global__ void build_active_kernel(Pathways pw, const int32_t* __restrict__ active, int k,
+                                    const int64_t* __restrict__ doff, const int64_t* __restrict__ eoff,
+                                    int32_t* __restrict__ pos, int32_t* __restrict__ diag_gene,
+                                    int32_t* __restrict__ diag_factor, double* __restrict__ diag_coef,
+                                    int32_t* __restrict__ off_r, int32_t* __restrict__ off_c,
+                                    int32_t* __restrict__ off_factor, double* __restrict__ off_coef) {
     const int c = blockIdx.y;
     const int p = active[c];
     const int64_t beg = pw.path_ptr[p], end = pw.path_ptr[p + 1];
-    for (int64_t r = beg + blockIdx.x * blockDim.x + threadIdx.x; r < end; r += (int64_t)gridDim.x * blockDim.x)
-        pos[(int64_t)pw.support_idx[r] * k + c] = (int32_t)r;
+    const int64_t ebeg = pw.row_ptr[beg];
+    for (int64_t r = beg + blockIdx.x * blockDim.x + threadIdx.x; r < end; r += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t g = pw.support_idx[r];
+        pos[(int64_t)g * k + c] = (int32_t)r;
+        const double ir = pw.isd[r];
+        const int64_t di = doff[c] + (r - beg);
+        diag_gene[di] = g;
+        diag_factor[di] = c;
+        diag_coef[di] = ir * (pw.ldiag[r] * ir);
+        for (int64_t e2 = pw.row_ptr[r]; e2 < pw.row_ptr[r + 1]; ++e2) {
+            const int64_t oi = eoff[c] + (e2 - ebeg);
+            const int64_t rc = beg + pw.col_local[e2];
+            off_r[oi] = g;
+            off_c[oi] = pw.support_idx[rc];
+            off_factor[oi] = c;
+            off_coef[oi] = (rc == r) ? 0.0 : ir * (-pw.w[e2] * pw.isd[rc]);
+        }
+    }
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -600,78 +636,83 @@ sum_gram_parts_kernel(const double* __restrict__ G_part, int blocks, int kk2, do
 //   recon^2 = ||X||^2 - 2 sum(V_new*B) + sum(Gu*Gv_new)        (B = X^T U_new, Gu = U_new^T U_new)
 //   manifold = sum_k vhat_k^T Lhat_{p_k} vhat_k ; ignore = sum_k sum_{i in supp} 1/(vhat_i + 1)
 //   fro = trace(Gu) = sum(U^2)
-// One block of 32 warps.  Gv_new entries are summed from the V-update partials (a warp per entry, or a
-// thread per entry when k*k is large); a warp per factor walks the active pathway.  Also publishes
-// Gv_new for the next step's U update.
+// One block of 1024 threads; every phase is one round of independent loads followed by a fixed-order
+// reduction.  Also publishes Gv_new = V_new^T V_new for the next step's U update.
 // ----------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 objective_kernel(const double* __restrict__ V, int n, int k, const double* __restrict__ red,
                  const double* __restrict__ Gv_part, const double* __restrict__ VB_part, int vblocks,
-                 const double* __restrict__ normX_sq, Pathways pw, const int32_t* __restrict__ active,
-                 double* __restrict__ Gv, double* __restrict__ gd, double tradeoff,
-                 double* __restrict__ obj_out, int* __restrict__ step_counter, int obj_capacity) {
+                 const double* __restrict__ normX_sq, ActiveSet as, double* __restrict__ Gv,
+                 double* __restrict__ gd, double tradeoff, double* __restrict__ obj_out,
+                 int* __restrict__ step_counter, int obj_capacity) {
     extern __shared__ double sm[];
-    double* sGv = sm;            // k*k
-    double* sMan = sm + k * k;   // k
-    double* sIgn = sMan + k;     // k
+    double* sGv = sm;                 // k*k
+    double* sSl = sm + k * k;         // <= 1024 slice sums
     __shared__ double scratch[32];
     const int kk2 = k * k;
     const int64_t nk = (int64_t)n * k;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    if (kk2 <= 512) {
-        for (int e = warp; e < kk2; e += nw) {
+    const int t = threadIdx.x;
+    // Gv_new[e] = sum over the V-update blocks' partials, in block order (slices, then slice sums in order)
+    if (kk2 <= 1024) {
+        const int nsl = 1024 / kk2;
+        const int per = (vblocks + nsl - 1) / nsl;
+        if (t < nsl * kk2) {
+            const int e = t % kk2, sl = t / kk2;
+            const int b0 = sl * per, cnt = max(0, min(vblocks, b0 + per) - b0);
+            sSl[sl * kk2 + e] = sum_strided(Gv_part + (int64_t)b0 * kk2 + e, cnt, kk2);
+        }
+        __syncthreads();
+        if (t < kk2) {
             double s = 0.0;
-            for (int b = lane; b < vblocks; b += 32) s += Gv_part[(int64_t)b * kk2 + e];
-            s = warp_sum(s);
-            if (lane == 0) { sGv[e] = s; Gv[e] = s; }
+            for (int sl = 0; sl < nsl; ++sl) s += sSl[sl * kk2 + t];
+            sGv[t] = s;
+            Gv[t] = s;
         }
     } else {
-        for (int e = threadIdx.x; e < kk2; e += blockDim.x) {
+        for (int e = t; e < kk2; e += blockDim.x) {
             const double s = sum_strided(Gv_part + e, vblocks, kk2);
-            sGv[e] = s; Gv[e] = s;
+            sGv[e] = s;
+            Gv[e] = s;
         }
     }
     __syncthreads();
-    double gg = 0.0;
-    for (int e = threadIdx.x; e < kk2; e += blockDim.x) gg = fma(sGv[e], red[nk + e], gg);
+    double gg = 0.0, fr = 0.0;
+    for (int e = t; e < kk2; e += blockDim.x) {
+        const double gu = red[nk + e];
+        gg = fma(sGv[e], gu, gg);
+        if (e / k == e % k) fr += gu;                                                       // :359
+    }
     double vb = 0.0;
-    for (int b = threadIdx.x; b < vblocks; b += blockDim.x) vb += VB_part[b];
-    const double GG = block_sum(gg, scratch);
-    const double VB = block_sum(vb, scratch);
-    // manifold / ignore: a warp per factor, lanes over the support rows of its active pathway
-    for (int c = warp; c < k; c += nw) {
-        const int p = active[c];
-        const int64_t beg = pw.path_ptr[p], end = pw.path_ptr[p + 1];
-        const double nrm = sqrt(sGv[c * k + c]);
-        double man = 0.0, ign = 0.0;
-        for (int64_t r = beg + lane; r < end; r += 32) {
-            const double vr = V[(int64_t)pw.support_idx[r] * k + c] / nrm;                 // :345
-            const double ir = pw.isd[r];
-            double y = (ir * (pw.ldiag[r] * ir)) * vr;                                      // diagonal of Lhat
-            for (int64_t e2 = pw.row_ptr[r]; e2 < pw.row_ptr[r + 1]; ++e2) {
-                const int cl = pw.col_local[e2];
-                if (beg + cl == r) continue;                                                // self loop is in ldiag
-                const double vc = V[(int64_t)pw.support_idx[beg + cl] * k + c] / nrm;
-                y = fma(ir * (-pw.w[e2] * pw.isd[beg + cl]), vc, y);
-            }
-            man = fma(y, vr, man);                                                          // :350
-            ign += 1.0 / (vr + 1.0);                                                        // :352
-        }
-        man = warp_sum(man); ign = warp_sum(ign);
-        if (lane == 0) { sMan[c] = man; sIgn[c] = ign; }
+    for (int b = t; b < vblocks; b += blockDim.x) vb += VB_part[b];
+    // manifold / ignore over the flattened normalised Laplacians of the active pathways
+    double man = 0.0, ign = 0.0;
+    for (int64_t i = t; i < as.n_diag; i += blockDim.x) {
+        const int c = as.diag_factor[i];
+        const double vr = V[(int64_t)as.diag_gene[i] * k + c] / sqrt(sGv[c * k + c]);       // :345
+        man = fma(as.diag_coef[i] * vr, vr, man);
+        ign += 1.0 / (vr + 1.0);                                                            // :352
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double MAN = 0.0, IGN = 0.0, fro = 0.0;
-        for (int c = 0; c < k; ++c) { MAN += sMan[c]; IGN += sIgn[c]; fro += red[nk + c * k + c]; }   // :359
+    for (int64_t i = t; i < as.n_off; i += blockDim.x) {
+        const int c = as.off_factor[i];
+        const double nrm = sqrt(sGv[c * k + c]);
+        const double vr = V[(int64_t)as.off_r[i] * k + c] / nrm;
+        const double vc = V[(int64_t)as.off_c[i] * k + c] / nrm;
+        man = fma(as.off_coef[i] * vc, vr, man);                                            // :350
+    }
+    const double GG = block_sum(gg, scratch);
+    const double FRO = block_sum(fr, scratch);
+    const double VB = block_sum(vb, scratch);
+    const double MAN = block_sum(man, scratch);
+    const double IGN = block_sum(ign, scratch);
+    if (t == 0) {
         const double gamma = gd[0], delta = gd[1];
         const double r2 = normX_sq[0] - 2.0 * VB + GG;
         const double recon = sqrt(r2 > 0.0 ? r2 : 0.0);
-        const double obj = recon + gamma * MAN + delta * IGN + fro;                         // :362
+        const double obj = recon + gamma * MAN + delta * IGN + FRO;                         // :362
         const int s = *step_counter;
         if (s < obj_capacity) {
             double* o = obj_out + (int64_t)s * kObjStride;
-            o[0] = recon; o[1] = MAN; o[2] = IGN; o[3] = fro; o[4] = obj; o[5] = gamma; o[6] = delta; o[7] = r2;
+            o[0] = recon; o[1] = MAN; o[2] = IGN; o[3] = FRO; o[4] = obj; o[5] = gamma; o[6] = delta; o[7] = r2;
         }
         *step_counter = s + 1;
         if (tradeoff >= 0.0) {                                                              // :542-548

@@ -61,6 +61,13 @@ struct prmf_handle {
     int obj_capacity = 0;
     int32_t *active = nullptr, *pos = nullptr;
     double* scores_buf = nullptr;             // 3 x k x P tables of prmf_scores
+    // flattened normalised Laplacians of the active pathways (objective)
+    ActiveSet as{};
+    int64_t as_cap_diag = 0, as_cap_off = 0;
+    int32_t *as_i32 = nullptr;                // [diag_gene | diag_factor | off_r | off_c | off_factor]
+    double* as_f64 = nullptr;                 // [diag_coef | off_coef]
+    int64_t* as_off = nullptr;                // doff[k+1] | eoff[k+1] on the device
+    std::vector<int64_t> row_ptr_host;
     bool have_X = false, have_UV = false, have_pw = false, have_active = false, pos_dirty = true;
     std::vector<int32_t> active_host;
 
@@ -265,7 +272,7 @@ int launch_xtu(prmf_handle* h) {
 size_t uu_smem(const prmf_handle* h) { return sizeof(double) * ((size_t)h->k * h->k + (size_t)h->uu_rows * h->k); }
 size_t vu_smem(const prmf_handle* h) { return sizeof(double) * ((size_t)h->k * h->k + (size_t)h->vu_rows * h->k); }
 size_t gram_smem(const prmf_handle* h) { return sizeof(double) * ((size_t)h->vu_rows * h->k); }
-size_t obj_smem(const prmf_handle* h) { return sizeof(double) * ((size_t)h->k * h->k + 2 * (size_t)h->k); }
+size_t obj_smem(const prmf_handle* h) { return sizeof(double) * ((size_t)h->k * h->k + 1024); }
 
 int launch_u_update(prmf_handle* h) {
     if (h->m == 0) {
@@ -300,10 +307,45 @@ int recompute_Gv(prmf_handle* h) {
 
 int ensure_pos(prmf_handle* h) {
     if (!h->pos_dirty) return PRMF_OK;
+    const int k = h->k;
+    // per-factor offsets into the flattened active set
+    std::vector<int64_t> offs(2 * (k + 1), 0);
+    for (int c = 0; c < k; ++c) {
+        const int p = h->active_host[c];
+        const int64_t beg = h->path_ptr_host[p], end = h->path_ptr_host[p + 1];
+        offs[c + 1] = offs[c] + (end - beg);
+        offs[k + 1 + c + 1] = offs[k + 1 + c] + (h->row_ptr_host[end] - h->row_ptr_host[beg]);
+    }
+    const int64_t nd = offs[k], no = offs[2 * k + 1];
+    if (nd > h->as_cap_diag || no > h->as_cap_off || !h->as_i32) {
+        CU(cudaStreamSynchronize(h->stream));
+        if (h->as_i32) cudaFree(h->as_i32);
+        if (h->as_f64) cudaFree(h->as_f64);
+        h->as_i32 = nullptr; h->as_f64 = nullptr;
+        h->as_cap_diag = std::max<int64_t>(nd * 2, 1024);
+        h->as_cap_off = std::max<int64_t>(no * 2, 4096);
+        int rc = dalloc(h, &h->as_i32, (size_t)(2 * h->as_cap_diag + 3 * h->as_cap_off));
+        if (rc) return rc;
+        if ((rc = dalloc(h, &h->as_f64, (size_t)(h->as_cap_diag + h->as_cap_off)))) return rc;
+    }
+    if (!h->as_off) { int rc = dalloc(h, &h->as_off, (size_t)2 * (k + 1)); if (rc) return rc; }
+    int32_t* dg = h->as_i32;
+    int32_t* df = dg + h->as_cap_diag;
+    int32_t* orr = df + h->as_cap_diag;
+    int32_t* occ = orr + h->as_cap_off;
+    int32_t* of = occ + h->as_cap_off;
+    double* dc = h->as_f64;
+    double* oc = dc + h->as_cap_diag;
+    CU(cudaMemcpyAsync(h->as_off, offs.data(), sizeof(int64_t) * offs.size(), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));      // offs is a stack-local host buffer
     CU(cudaMemsetAsync(h->pos, 0xff, sizeof(int32_t) * h->n * h->k, h->stream));
     dim3 grid(4, h->k);
-    build_pos_kernel<<<grid, 128, 0, h->stream>>>(h->pw, h->active, h->k, h->pos);
-    LAUNCH_CHECK("build_pos_kernel");
+    build_active_kernel<<<grid, 128, 0, h->stream>>>(h->pw, h->active, k, h->as_off, h->as_off + (k + 1), h->pos, dg, df,
+                                                     dc, orr, occ, of, oc);
+    LAUNCH_CHECK("build_active_kernel");
+    h->as.n_diag = nd; h->as.n_off = no;
+    h->as.diag_gene = dg; h->as.diag_factor = df; h->as.diag_coef = dc;
+    h->as.off_r = orr; h->as.off_c = occ; h->as.off_factor = of; h->as.off_coef = oc;
     h->pos_dirty = false;
     return PRMF_OK;
 }
@@ -392,7 +434,7 @@ int enqueue_steps(prmf_handle* h, int n_steps, double gamma, double delta, doubl
         if (rc) return rc;
         tic(5);
         objective_kernel<<<1, 1024, obj_smem(h), h->stream>>>(h->Vbuf[h->vcur], (int)h->n, h->k, h->red, h->Gv_part,
-                                                              h->VB_part, h->vu_grid, h->normX_sq, h->pw, h->active,
+                                                              h->VB_part, h->vu_grid, h->normX_sq, h->as,
                                                               h->Gv, h->gd, tradeoff, h->obj, h->step_counter,
                                                               h->obj_capacity);
         LAUNCH_CHECK("objective_kernel");
@@ -582,7 +624,7 @@ int prmf_destroy(prmf_handle* h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     void* bufs[] = {h->X, h->Xt, h->U, h->Vbuf[0], h->Vbuf[1], h->Ub, h->Vb, h->Gvb, h->Apart, h->Gv, h->Gu_part,
                     h->Gv_part, h->VB_part, h->Bpart, h->red, h->normX_sq, h->scal_part, h->gd, h->obj,
-                    h->step_counter, h->active, h->pos, h->scores_buf};
+                    h->step_counter, h->active, h->pos, h->scores_buf, h->as_i32, h->as_f64, h->as_off};
     for (void* b : bufs) if (b) cudaFree(b);
     for (void* b : h->pw_allocs) cudaFree(b);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -687,6 +729,7 @@ int prmf_set_pathways(prmf_handle* h, int32_t P, const int64_t* path_ptr, const 
     if ((rc = dalloc(h, &h->scores_buf, (size_t)3 * h->k * P))) return rc;
     h->pw = pw; h->S = S; h->E = E;
     h->path_ptr_host.assign(path_ptr, path_ptr + P + 1);
+    h->row_ptr_host.assign(row_ptr, row_ptr + S + 1);
     h->have_pw = true;
     h->have_active = false;
     h->pos_dirty = true;

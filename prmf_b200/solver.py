@@ -58,27 +58,64 @@ def _current_device():
 # ----------------------------------------------------------------------------------------------------
 def init_latent_to_pathway_data(k_latent, n_pathways):
     """Every pathway is a candidate of every factor with score 1 (:196-200)."""
-    return {k: [(p, 1) for p in range(n_pathways)] for k in range(k_latent)}
+    ids, ones = np.arange(n_pathways, dtype=np.int64), np.ones(n_pathways)
+    return {k: _CandArrays(ids, ones, [(p, 1) for p in range(n_pathways)]) for k in range(k_latent)}
 
 
 def count_distinct_pathways(latent_to_pathway_data):
     return min(len(v) for v in latent_to_pathway_data.values())            # :203-207
 
 
+def _ids_scores(data):
+    """Candidate list [(pathway, score), ...] -> (int64 ids, float64 scores)."""
+    if isinstance(data, _CandArrays):
+        return data.ids, data.scores
+    ids = np.fromiter((p for p, _ in data), dtype=np.int64, count=len(data))
+    scores = np.fromiter((s for _, s in data), dtype=np.float64, count=len(data))
+    return ids, scores
+
+
+class _CandArrays(list):
+    """A candidate list that also carries its (ids, scores) as arrays, so the per-iteration host work
+    is a handful of vector operations.  It still is the reference's list of (pathway, score) tuples."""
+
+    def __init__(self, ids, scores, as_list=None):
+        super().__init__(zip(ids.tolist(), scores) if as_list is None else as_list)
+        self.ids, self.scores = ids, scores
+
+
 def sample_active(latent_to_pathway_data, k_latent):
     """One multinomial draw per factor from the global legacy NumPy RNG, in factor order (:717-730).
-    `scipy.stats.multinomial.rvs(1, p)` draws exactly `np.random.multinomial(1, p)`."""
+    `scipy.stats.multinomial.rvs(1, p)` draws exactly `np.random.multinomial(1, p)` (the last
+    probability is implied), and a single-candidate draw consumes no random numbers in either."""
     active = []
     for k in range(k_latent):
-        ids = [p for p, _ in latent_to_pathway_data[k]]
-        scores = np.array([s for _, s in latent_to_pathway_data[k]])
+        ids, scores = _ids_scores(latent_to_pathway_data[k])
         with np.errstate(divide="raise", invalid="raise"):                  # np.seterr(divide='raise'), :22
             prob = scores / np.sum(scores)
-        prob = np.array(prob, dtype=np.float64)
-        prob[-1] = 1.0 - prob[:-1].sum()                                    # scipy's _process_parameters
         draw = np.random.multinomial(1, prob)
-        active.append(ids[int(np.where(draw != 0)[0][0])])
+        active.append(int(ids[int(np.flatnonzero(draw)[0])]))
     return active
+
+
+_Q199 = np.true_divide(PERCENTILE, np.float64(100))
+
+
+def percentile_19_9(x):
+    """`np.percentile(x, 19.9)` for a 1-D float64 array (method 'linear'), without numpy's per-call
+    overhead: virtual index (n-1)*q, the two neighbouring order statistics, numpy's `_lerp`.
+    tests/test_host_logic.py checks bit-for-bit agreement with np.percentile."""
+    n = x.shape[0]
+    vi = (n - 1) * _Q199
+    lo = int(math.floor(vi))
+    hi = min(lo + 1, n - 1)
+    g = vi - lo
+    part = np.partition(x, (lo, hi))
+    a, b = part[lo], part[hi]
+    diff = b - a
+    if g >= 0.5:
+        return b - diff * (1 - g)
+    return a + diff * g
 
 
 def restrict_from_tables(mass, quad_norm, latent_to_pathway_data):
@@ -88,15 +125,15 @@ def restrict_from_tables(mass, quad_norm, latent_to_pathway_data):
     for k in sorted(latent_to_pathway_data):
         data = latent_to_pathway_data[k]
         if len(data) > 1:
-            ids = np.array([p for p, _ in data])
+            ids, _ = _ids_scores(data)
             scores = np.sqrt(mass[k, ids]) + (1 - quad_norm[k, ids])        # :123-125
-            keep = np.where(scores > np.percentile(scores, PERCENTILE))[0]  # :171
+            keep = np.flatnonzero(scores > percentile_19_9(scores))         # :171
             if len(keep) == 0:
                 # the reference falls into np.random.choice(size=ceil(n*(1-19.9)/100) < 0) and raises
                 raise ValueError("restrict: all %d candidate scores of factor %d are equal; the "
                                  "reference's fallback (prmf_runner.py:173-183) raises here too"
                                  % (len(ids), k))
-            out[k] = [(int(ids[i]), scores[i]) for i in keep]
+            out[k] = _CandArrays(ids[keep], scores[keep])
         else:
             out[k] = data
     return out
@@ -107,11 +144,9 @@ def force_distinct_from_tables(quad_raw, V, supports, active, latent_to_pathway_
     weight 1/(gamma * v^T L v + delta * ign).  `ign` is the ignore penalty of the LAST factor only --
     the reference overwrites instead of accumulating (:234-235) -- and is kept that way."""
     import networkx as nx
-    k_last = max(latent_to_pathway_data)
     ign = 0
     for k2 in sorted(latent_to_pathway_data):
         ign = np.sum(np.power(V[supports[active[k2]], k2] + 1, -1))
-    del k_last
     G = nx.Graph()
     for k, data in latent_to_pathway_data.items():
         for p, _ in data:

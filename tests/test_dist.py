@@ -1,0 +1,81 @@
+"""N > 1 path: rows of X and U sharded over ranks, partial X^T U / U^T U summed over ranks.
+
+CPU (gloo, world_size 2, numpy stand-in engine): the host logic -- sharding, identical RNG streams and
+decisions on every rank, gather of U -- reproduces the reference fixture.
+GPU (nccl, needs >= 2 devices): the CUDA engines with the in-library NCCL all-reduce do the same."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+WORKER = os.path.join(ROOT, "tests", "mp_worker.py")
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _run(case, tmp_path, world, mode):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), WORKER, case, str(tmp_path), mode]
+    env = dict(os.environ, OMP_NUM_THREADS="2", OPENBLAS_NUM_THREADS="2")
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    return [np.load(os.path.join(tmp_path, "rank%d.npz" % r)) for r in range(world)]
+
+
+def _check(case, outs, rtol_obj, rtol_uv):
+    g = load_golden(case)
+    meta = g["meta"]
+    for z in outs:
+        assert z["sampled"].tolist() == meta["sampled"]
+        assert z["obj_parts"].shape == g["obj_parts"].shape
+        np.testing.assert_allclose(z["obj_parts"], g["obj_parts"], rtol=rtol_obj, atol=1e-11)
+        np.testing.assert_allclose(z["U"], g["U_final"], rtol=rtol_uv, atol=1e-10)
+        np.testing.assert_allclose(z["V"], g["V_final"], rtol=rtol_uv, atol=1e-10)
+        fm = {k: [p for p, _ in v] for k, v in meta["final_map"].items()}
+        assert json.loads(str(z["fmap"])) == fm
+    for z in outs[1:]:                      # every rank returns the same full result, bit for bit
+        np.testing.assert_array_equal(z["U"], outs[0]["U"])
+        np.testing.assert_array_equal(z["V"], outs[0]["V"])
+
+
+@pytest.mark.parametrize("case", ["small_tradeoff", "test2_raw"])
+def test_two_ranks_gloo_host_logic(case, tmp_path):
+    outs = _run(case, tmp_path, 2, "cpu")
+    _check(case, outs, rtol_obj=1e-9, rtol_uv=1e-6)
+
+
+def test_three_ranks_gloo_ragged_shards(tmp_path):
+    """40 rows over 3 ranks -> 14 + 14 + 12."""
+    outs = _run("small_tradeoff", tmp_path, 3, "cpu")
+    _check("small_tradeoff", outs, rtol_obj=1e-9, rtol_uv=1e-6)
+
+
+def test_row_block_partition():
+    from prmf_b200.dist import row_block
+    for m, w in [(37032, 8), (10, 3), (5, 8), (100, 1), (0, 2)]:
+        blocks = [row_block(m, w, r) for r in range(w)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == m
+        for (a, b), (c, d) in zip(blocks[:-1], blocks[1:]):
+            assert b == c and a <= b and c <= d
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["small_planted", "test1_norm"])
+def test_two_gpus_nccl(case, tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    outs = _run(case, tmp_path, 2, "gpu")
+    _check(case, outs, rtol_obj=1e-9, rtol_uv=1e-6)

@@ -198,5 +198,48 @@ def main():
     save_kernel_vectors()
 
 
+
+
+# ---- CLI golden (appended): run the reference's own main() on the files of its test ------------------
+from make_golden_io import write_cli_inputs  # noqa: E402
+
+
+def save_cli_case():
+    import shutil
+    import tempfile
+    R = ref_shim.load_reference()
+    X, nodelist, Gs = synth.test1_instance()
+    tmp = tempfile.mkdtemp()
+    cwd = os.getcwd()
+    try:
+        fps = write_cli_inputs(tmp, X, nodelist, Gs)
+        os.chdir(tmp)
+        rel = [os.path.basename(f) for f in fps]
+        for tag, extra in (("nonorm", ["--no-normalize"]), ("norm", [])):
+            ref_shim.reset_globals(R)
+            argv = ["prmf_runner.py", "--data", "data.tsv", "--manifolds"] + rel + [
+                "--node-attribute", "name", "--nodelist", "nodelist.txt", "--outdir", ".", "--delimiter", "\t",
+                "--seed", "1"] + extra
+            old = sys.argv
+            sys.argv = argv
+            try:
+                with contextlib.redirect_stdout(io.StringIO()) as out, contextlib.redirect_stderr(io.StringIO()):
+                    R.main()
+            finally:
+                sys.argv = old
+            dst = os.path.join(HERE, "cli_test1_" + tag)
+            os.makedirs(dst, exist_ok=True)
+            for f in ("obj.txt", "U.csv", "V.csv"):
+                shutil.copy(os.path.join(tmp, f), os.path.join(dst, f))
+            with open(os.path.join(dst, "stdout_head.txt"), "w") as fh:
+                fh.write("\n".join(out.getvalue().splitlines()[:12]) + "\n")
+            print("cli_test1_%-21s %s" % (tag, open(os.path.join(dst, "obj.txt")).read().splitlines()[6]))
+    finally:
+        os.chdir(cwd)
+        shutil.rmtree(tmp)
+
+
 if __name__ == "__main__":
-    main()
+    if "--cli-only" not in sys.argv:
+        main()
+    save_cli_case()

@@ -75,13 +75,28 @@ def _ids_scores(data):
     return ids, scores
 
 
-class _CandArrays(list):
-    """A candidate list that also carries its (ids, scores) as arrays, so the per-iteration host work
-    is a handful of vector operations.  It still is the reference's list of (pathway, score) tuples."""
+class _CandArrays:
+    """The reference's candidate list [(pathway, score), ...] held as two arrays; tuples are made only when
+    somebody iterates or indexes (verbose printing, traces, the returned obj_data)."""
+    __slots__ = ("ids", "scores", "_fixed")
 
     def __init__(self, ids, scores, as_list=None):
-        super().__init__(zip(ids.tolist(), scores) if as_list is None else as_list)
-        self.ids, self.scores = ids, scores
+        self.ids, self.scores, self._fixed = ids, scores, as_list
+
+    def __len__(self):
+        return self.ids.shape[0]
+
+    def __iter__(self):
+        return iter(self._fixed) if self._fixed is not None else zip(self.ids.tolist(), self.scores)
+
+    def __getitem__(self, i):
+        return list(self)[i]
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+    def __repr__(self):
+        return repr(list(self))
 
 
 def sample_active(latent_to_pathway_data, k_latent):
@@ -317,7 +332,11 @@ def nmf_pathway(X, Gs, gamma=1.0, delta=1.0, tradeoff=None, k_latent=6, tol=1e-3
                     out(k, p)
                 out("--------------------------------------------")
             eng.set_active(active)
-            parts, g2, d2 = eng.step(modulus, gamma, delta, tradeoff)      # :739-742
+            # :739-742 -- the 10 steps and (while candidates remain) the score tables are enqueued back to
+            # back; the host waits once
+            eng.step_async(modulus, gamma, delta, tradeoff)
+            tables = eng.scores() if candidates_remain else None
+            parts, g2, d2 = eng.step_collect(modulus)
             for s in range(modulus):
                 out(i + s + 1, float(parts[s, 4]))                         # :447
                 if verbose:
@@ -335,7 +354,7 @@ def nmf_pathway(X, Gs, gamma=1.0, delta=1.0, tradeoff=None, k_latent=6, tol=1e-3
             kind = None
             if candidates_remain:                                          # :754-768
                 if count_distinct_pathways(cands) <= k_latent:
-                    _, _, quad_raw = eng.scores()
+                    quad_raw = tables[2]
                     _, V_now = eng.get_UV(want_U=False)
                     cands = force_distinct_from_tables(quad_raw, V_now, packed.supports, active, cands,
                                                        gamma, delta)
@@ -344,8 +363,7 @@ def nmf_pathway(X, Gs, gamma=1.0, delta=1.0, tradeoff=None, k_latent=6, tol=1e-3
                 else:
                     if ctx.rank == 0:
                         sys.stderr.write("Before restrict: " + str(datetime.datetime.now()) + "\n")
-                    mass, quad_norm, _ = eng.scores()
-                    cands = restrict_from_tables(mass, quad_norm, cands)
+                    cands = restrict_from_tables(tables[0], tables[1], cands)
                     if ctx.rank == 0:
                         sys.stderr.write("After restrict: " + str(datetime.datetime.now()) + "\n")
                     candidates_remain = any(len(v) > 1 for v in cands.values())
@@ -374,7 +392,7 @@ def nmf_pathway(X, Gs, gamma=1.0, delta=1.0, tradeoff=None, k_latent=6, tol=1e-3
         eng.close()
     U = ctx.all_gather_rows(U_local, m)
     obj_data = dict(obj_data)
-    obj_data["latent_to_pathway_data"] = cands
+    obj_data["latent_to_pathway_data"] = {k: list(v) for k, v in cands.items()}
     return U, V, obj_data
 
 

@@ -108,6 +108,12 @@ class NumpyShardEngine:
                 delta = gamma
         return parts, gamma, delta
 
+    def step_async(self, n_steps, gamma, delta, tradeoff=None):
+        self._pending = self.step(n_steps, gamma, delta, tradeoff)
+
+    def step_collect(self, n_steps):
+        return self._pending
+
     def scores(self):
         K, P = self.k, self.P
         mass = np.zeros((K, P)); qn = np.zeros((K, P)); qr = np.zeros((K, P))

@@ -404,6 +404,120 @@ skinny_tma_kernel(const double* __restrict__ M, int64_t ldm, int64_t rows_total,
     }
 }
 
+// ----------------------------------------------------------------------------------------------------
+// General-k TMA X-stream kernel (k > 10: BASELINE configs 4 and 5).  Same pipeline as skinny_tma_kernel; the
+// 256 consumer threads are split into FG factor groups of 256/FG threads.  A thread owns 4 columns of a
+// (1024/FG)-column panel and KT consecutive factors of its group, so the X tile is fetched from HBM once and
+// re-read from shared memory by every group -- at k = 64 the kernel is FP64-FMA bound (16 flop per byte of X),
+// not HBM bound.  k is a run-time value; factors >= k of the last group are computed on in-bounds garbage
+// and never written.
+// ----------------------------------------------------------------------------------------------------
+template <int KT, int FG, int RS>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+skinny_tma_gen_kernel(const double* __restrict__ M, int64_t ldm, int64_t rows_total, int64_t cols,
+                      const double* __restrict__ W, int k, int panel_w, int64_t rows_per_chunk, int stages,
+                      double* __restrict__ OutPart) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int TG = 256 / FG;                                          // threads per factor group
+    const int panel = blockIdx.x;
+    const int64_t chunk = blockIdx.y;
+    const int64_t c0 = (int64_t)panel * panel_w;
+    const int width = (int)min((int64_t)panel_w, ldm - c0);
+    const uint32_t row_bytes = (uint32_t)width * 8u;
+    const uint32_t x_stage_bytes = (uint32_t)RS * (uint32_t)panel_w * 8u;
+    const uint32_t w_bytes = (uint32_t)RS * (uint32_t)k * 8u;
+    const uint32_t w_slot = (((uint32_t)RS * (uint32_t)k + KT) * 8u + 127u) & ~127u;   // + KT doubles of slack
+    const uint32_t stage_bytes = x_stage_bytes + w_slot;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + stages;
+    const int64_t rbeg = chunk * rows_per_chunk;
+    const int64_t rend = min(rows_total, rbeg + rows_per_chunk);
+    const int nstage_iters = rend > rbeg ? (int)((rend - rbeg + RS - 1) / RS) : 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s2 = 0; s2 < stages; ++s2) {
+            mbar_init(&full_bar[s2], 1);
+            mbar_init(&empty_bar[s2], kTmaConsumerWarps);
+        }
+        fence_mbar_init();
+    }
+    // the slack behind every W slot is read (and discarded) by the last factor group: keep it finite
+    for (int s2 = threadIdx.x; s2 < stages * KT; s2 += blockDim.x)
+        reinterpret_cast<double*>(smem_raw + (size_t)(s2 / KT) * stage_bytes + x_stage_bytes + w_bytes)[s2 % KT] = 0.0;
+    __syncthreads();
+
+    if (warp == kTmaConsumerWarps) {
+        const uint64_t pol_x = l2_policy_evict_first();
+        const uint64_t pol_w = l2_policy_evict_last();
+        int s2 = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < nstage_iters; ++it) {
+            const int64_t r0 = rbeg + (int64_t)it * RS;
+            const int rows = (int)min((int64_t)RS, rend - r0);
+            if (lane == 0) mbar_wait(&empty_bar[s2], phase ^ 1u);
+            __syncwarp();
+            unsigned char* sx = smem_raw + (size_t)s2 * stage_bytes;
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&full_bar[s2], (uint32_t)rows * row_bytes + w_bytes);
+                bulk_g2s(sx + x_stage_bytes, W + r0 * k, w_bytes, &full_bar[s2], pol_w);
+            }
+            __syncwarp();
+            if (lane < rows)
+                bulk_g2s(sx + (size_t)lane * panel_w * 8, M + (r0 + lane) * ldm + c0, row_bytes, &full_bar[s2], pol_x);
+            if (++s2 == stages) { s2 = 0; phase ^= 1u; }
+        }
+        return;
+    }
+
+    const int H = panel_w >> 2;
+    const int fg = threadIdx.x / TG, t = threadIdx.x % TG;
+    const int f0 = fg * KT;                                               // first factor of this thread
+    const bool active = t < H && (2 * t) < width;
+    const bool active2 = t < H && (2 * (t + H)) < width;
+    double acc[4][KT];
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int c = 0; c < KT; ++c) acc[g][c] = 0.0;
+    int s2 = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < nstage_iters; ++it) {
+        const int rows = (int)min((int64_t)RS, rend - (rbeg + (int64_t)it * RS));
+        mbar_wait(&full_bar[s2], phase);
+        const unsigned char* sx = smem_raw + (size_t)s2 * stage_bytes;
+        const double* sw = reinterpret_cast<const double*>(sx + x_stage_bytes) + f0;
+        for (int r = 0; r < rows; ++r) {
+            const double2* xrow = reinterpret_cast<const double2*>(sx + (size_t)r * panel_w * 8);
+            const double2 xa = active ? xrow[t] : make_double2(0.0, 0.0);
+            const double2 xb = active2 ? xrow[t + H] : make_double2(0.0, 0.0);
+            const double* wr = sw + r * k;
+#pragma unroll
+            for (int c = 0; c < KT; ++c) {
+                const double u = wr[c];
+                acc[0][c] = fma(xa.x, u, acc[0][c]);
+                acc[1][c] = fma(xa.y, u, acc[1][c]);
+                acc[2][c] = fma(xb.x, u, acc[2][c]);
+                acc[3][c] = fma(xb.y, u, acc[3][c]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s2]);
+        if (++s2 == stages) { s2 = 0; phase ^= 1u; }
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int64_t j = c0 + 2 * (int64_t)(g < 2 ? t : t + H) + (g & 1);
+        const bool ok = (g < 2 ? active : active2) && j < cols;
+        if (ok) {
+            double* out = OutPart + ((int64_t)chunk * cols + j) * k + f0;
+#pragma unroll
+            for (int c = 0; c < KT; ++c)
+                if (f0 + c < k) out[c] = acc[g][c];
+        }
+    }
+}
+
 // Xt[j][i] = X[i][j] : the factor of 2 in HBM capacity buys a coalesced, reduction-free pass 1.
 __global__ void __launch_bounds__(256)
 transpose_kernel(const double* __restrict__ X, int64_t ldx, int64_t m, int64_t n, double* __restrict__ Xt,

@@ -87,6 +87,7 @@ struct prmf_handle {
     int ktile = 0, nq = 1;
     // TMA (bulk-async) variant of the X-stream kernel: used when one factor tile covers k
     bool use_tma = false;
+    int tma_fg = 1, tma_kt = 0;               // factor groups / factors per thread of the general-k kernel
     int tma_rs = 8, tma_stages = 3;
     int tpanels1 = 0, tpanel_w1 = 0, tchunks1 = 0, tpanels = 0, tpanel_w = 0, tchunks = 0;
     int64_t trows_per_chunk1 = 0, trows_per_chunk = 0;
@@ -162,7 +163,8 @@ int pick_nq(int k) {
 
 template <typename F>
 int set_smem(prmf_handle* h, F kernel, size_t bytes) {
-    if (bytes > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    // static shared memory counts against the 48 KB default too, so opt in with some margin
+    if (bytes > 40 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return PRMF_OK;
 }
 
@@ -204,6 +206,27 @@ int launch_skinny_tma_t(prmf_handle* h, const double* M, int64_t ldm, int64_t ro
     return PRMF_OK;
 }
 
+template <int KT, int FG>
+int launch_skinny_gen_t(prmf_handle* h, const double* M, int64_t ldm, int64_t rows, int64_t cols, const double* W,
+                        int panels, int panel_w, int chunks, int64_t rows_per_chunk, size_t smem, double* out) {
+    dim3 grid(panels, chunks);
+    CU(cudaFuncSetAttribute(skinny_tma_gen_kernel<KT, FG, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    skinny_tma_gen_kernel<KT, FG, 8><<<grid, kTmaThreads, smem, h->stream>>>(M, ldm, rows, cols, W, h->k, panel_w,
+                                                                             rows_per_chunk, h->tma_stages, out);
+    return PRMF_OK;
+}
+
+int launch_skinny_gen(prmf_handle* h, const double* M, int64_t ldm, int64_t rows, int64_t cols, const double* W,
+                      int panels, int panel_w, int chunks, int64_t rows_per_chunk, size_t smem, double* out) {
+#define GEN_CASE(KT_, FG_) \
+    if (h->tma_kt == KT_ && h->tma_fg == FG_) \
+        return launch_skinny_gen_t<KT_, FG_>(h, M, ldm, rows, cols, W, panels, panel_w, chunks, rows_per_chunk, smem, out);
+    GEN_CASE(12, 1) GEN_CASE(16, 1) GEN_CASE(8, 2) GEN_CASE(12, 2) GEN_CASE(16, 2) GEN_CASE(8, 4) GEN_CASE(12, 4)
+    GEN_CASE(16, 4) GEN_CASE(8, 8) GEN_CASE(12, 8) GEN_CASE(16, 8)
+#undef GEN_CASE
+    return fail(h, PRMF_ERR_STATE, "no general-k kernel for KT=%d FG=%d", h->tma_kt, h->tma_fg);
+}
+
 #define KT_SWITCH_RC(kt, rc, FN, ...)          \
     switch (kt) {                              \
         case 1: rc = FN<1>(__VA_ARGS__); break;   \
@@ -223,8 +246,13 @@ int launch_xv(prmf_handle* h) {
     if (h->m == 0) return PRMF_OK;
     if (h->use_tma) {
         int rc = 0;
-        KT_SWITCH_RC(h->k, rc, launch_skinny_tma_t, h, h->Xt, h->ldxt, h->n, h->m, h->Vbuf[h->vcur], h->tpanels1,
-                     h->tpanel_w1, h->tchunks1, h->trows_per_chunk1, h->tma_smem1, h->Apart);
+        if (h->k > 10) {
+            rc = launch_skinny_gen(h, h->Xt, h->ldxt, h->n, h->m, h->Vbuf[h->vcur], h->tpanels1, h->tpanel_w1,
+                                   h->tchunks1, h->trows_per_chunk1, h->tma_smem1, h->Apart);
+        } else {
+            KT_SWITCH_RC(h->k, rc, launch_skinny_tma_t, h, h->Xt, h->ldxt, h->n, h->m, h->Vbuf[h->vcur], h->tpanels1,
+                         h->tpanel_w1, h->tchunks1, h->trows_per_chunk1, h->tma_smem1, h->Apart);
+        }
         if (rc) return rc;
         LAUNCH_CHECK("skinny_tma_kernel(pass 1)");
         return PRMF_OK;
@@ -246,8 +274,13 @@ int launch_xtu(prmf_handle* h) {
     }
     if (h->use_tma) {
         int rc = 0;
-        KT_SWITCH_RC(h->k, rc, launch_skinny_tma_t, h, h->X, h->ldx, h->m, h->n, h->U, h->tpanels, h->tpanel_w,
-                     h->tchunks, h->trows_per_chunk, h->tma_smem2, h->Bpart);
+        if (h->k > 10) {
+            rc = launch_skinny_gen(h, h->X, h->ldx, h->m, h->n, h->U, h->tpanels, h->tpanel_w, h->tchunks,
+                                   h->trows_per_chunk, h->tma_smem2, h->Bpart);
+        } else {
+            KT_SWITCH_RC(h->k, rc, launch_skinny_tma_t, h, h->X, h->ldx, h->m, h->n, h->U, h->tpanels, h->tpanel_w,
+                         h->tchunks, h->trows_per_chunk, h->tma_smem2, h->Bpart);
+        }
         if (rc) return rc;
         LAUNCH_CHECK("skinny_tma_kernel(pass 2)");
         return PRMF_OK;
@@ -547,16 +580,25 @@ int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global
         const char* e1 = getenv("PRMF_TMA");
         const char* e2 = getenv("PRMF_TMA_RS");
         const char* e3 = getenv("PRMF_TMA_STAGES");
-        h->use_tma = (k <= 10) && !(e1 && atoi(e1) == 0);
-        if (e2 && atoi(e2) == 4) h->tma_rs = 4;
+        h->use_tma = !(e1 && atoi(e1) == 0);
+        if (e2 && atoi(e2) == 4 && k <= 10) h->tma_rs = 4;
         if (e3 && atoi(e3) >= 2 && atoi(e3) <= 12) h->tma_stages = atoi(e3);
+        if (k > 10) {                      // general-k kernel: FG factor groups x KT factors per thread
+            const int groups = (k + 15) / 16;
+            h->tma_fg = groups <= 1 ? 1 : groups <= 2 ? 2 : groups <= 4 ? 4 : 8;
+            const int per = (k + h->tma_fg - 1) / h->tma_fg;
+            h->tma_kt = per <= 8 ? 8 : per <= 12 ? 12 : 16;
+            if (!e3) h->tma_stages = h->tma_fg >= 4 ? 6 : h->tma_fg == 2 ? 4 : 3;
+        }
+        const int64_t max_panel = 1024 / h->tma_fg;
         auto plan = [&](int64_t cols, int64_t rows, int* panels, int* panel_w, int* chunks, int64_t* rpc, size_t* smem) {
-            *panels = (int)std::max<int64_t>(1, (cols + 1023) / 1024);
+            *panels = (int)std::max<int64_t>(1, (cols + max_panel - 1) / max_panel);
             *panel_w = (int)round_up((std::max<int64_t>(1, cols) + *panels - 1) / *panels, 4);
             *chunks = std::max(1, h->sm_count / *panels);
             *chunks = (int)std::min<int64_t>(*chunks, std::max<int64_t>(1, rows / (4 * h->tma_rs)));
             *rpc = round_up(std::max<int64_t>(1, (rows + *chunks - 1) / *chunks), h->tma_rs);
-            const size_t xb = (size_t)h->tma_rs * *panel_w * 8, wb = ((size_t)h->tma_rs * k * 8 + 127) & ~(size_t)127;
+            const size_t xb = (size_t)h->tma_rs * *panel_w * 8;
+            const size_t wb = (((size_t)h->tma_rs * k + 16) * 8 + 127) & ~(size_t)127;
             *smem = h->tma_stages * (xb + wb) + 2 * h->tma_stages * sizeof(uint64_t);
         };
         plan(m_local, n, &h->tpanels1, &h->tpanel_w1, &h->tchunks1, &h->trows_per_chunk1, &h->tma_smem1);

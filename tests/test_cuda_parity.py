@@ -37,7 +37,11 @@ def _instance(m, n, k, P, seed, weighted=False, psize=12):
     (200, 517, 10, 12),    # the benchmark's k
     (96, 300, 12, 6),      # k > 10: two factor tiles
     (70, 210, 17, 6),      # k > 16: pairs-per-thread > 1
-    (50, 120, 33, 4),      # larger k
+    (50, 120, 33, 4),      # larger k: 4 factor groups x 12
+    (40, 300, 16, 5),      # one group of 16
+    (64, 2100, 64, 6),     # BASELINE config 4's k: 4 groups x 16, several panels
+    (33, 150, 100, 4),     # 8 groups, ragged last group
+    (24, 140, 128, 3),     # BASELINE config 5's k
 ])
 @pytest.mark.parametrize("weighted", [False, True])
 def test_inner_steps_match_oracle(m, n, k, P, weighted):

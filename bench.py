@@ -74,6 +74,18 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.path = None
+        self.begin = 0
+
+    def _lines(self):
+        try:
+            with open(self.path) as fh:
+                return fh.readlines()
+        except Exception:
+            return []
+
+    def mark_begin(self):
+        """Samples before this point (set-up, warm-up) are not part of the timed region."""
+        self.begin = len(self._lines())
 
     def start(self):
         try:
@@ -81,7 +93,7 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "20"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -96,7 +108,9 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons, power = [], [], set(), []
         try:
-            for line in open(self.path):
+            lines = self._lines()
+            lines = lines[self.begin:] if len(lines) > self.begin else lines[-3:]
+            for line in lines:
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 9:
                     continue
@@ -208,6 +222,8 @@ def run_ours(a):
         raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (a.gpus, ctx.world))
     dev = ctx.local_rank if ctx.world > 1 else 0
     torch.cuda.set_device(dev)
+    sampler = ClockSampler(dev)
+    sampler.start()                      # nvidia-smi needs ~1 s to come up: start it before the data setup
     stream = torch.cuda.Stream(device=dev)
     lo, hi = row_block(a.m, ctx.world, ctx.rank)
     m_local = hi - lo
@@ -253,15 +269,11 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(dev)
-    sampler.start()                      # nvidia-smi needs ~1 s to start; sample from the warm-up on
-    t_w = time.perf_counter()
-    for _ in range(a.warmup):
-        outer_iteration()
-    while time.perf_counter() - t_w < 1.5:   # keep the GPU under the same load until the sampler is live
+    for _ in range(a.warmup):            # NOTE: the same number of steps on every rank (each holds collectives)
         outer_iteration()
     launches0 = eng.launch_count
     sync_all()
+    sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # ---- timed region: exactly K steps, device events on the launching stream, max over ranks ----
     host_t[0] = 0.0
@@ -404,6 +416,8 @@ def run_ours(a):
 T_START = time.perf_counter()
 
 if __name__ == "__main__":
+    import faulthandler
+    faulthandler.dump_traceback_later(420, exit=True)     # never hang a GPU box: die loudly instead
     args = parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

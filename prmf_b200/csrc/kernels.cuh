@@ -129,25 +129,104 @@ __global__ void sum_partials_kernel(const double* __restrict__ part, int count, 
 }
 
 // ----------------------------------------------------------------------------------------------------
+// Gram accumulation shared by the U and V update kernels: G += T^T T for a tile T (rows x k) held in shared
+// memory.  The k*k pairs are split over the 1024 threads; when k*k < 1024 the rows of the tile are also cut
+// into NS slices so every thread has work (item = slice * k*k + pair).  Slices are combined in a fixed order.
+// ----------------------------------------------------------------------------------------------------
+constexpr int kTailThreads = 1024;
+
+__host__ __device__ inline int gram_slices(int k) {
+    const int kk2 = k * k;
+    if (kk2 >= kTailThreads) return 1;
+    int ns = kTailThreads / kk2;
+    return ns > 8 ? 8 : ns;
+}
+
+// dst[e] = sum_b src[b*kk2 + e] (b < count) for a k*k matrix, using all 1024 threads: the partials are cut into
+// 1024/kk2 slices that are summed concurrently, then the slice sums are added in order.  sBuf: >= 1024 doubles.
+__device__ __forceinline__ void sum_gram_partials(double* __restrict__ dst, const double* __restrict__ src, int count,
+                                                  int kk2, double* __restrict__ sBuf) {
+    if (kk2 > 512 || count <= 8) {
+        for (int e = threadIdx.x; e < kk2; e += blockDim.x) dst[e] = sum_strided(src + e, count, kk2);
+        __syncthreads();
+        return;
+    }
+    const int nsl = 1024 / kk2;
+    const int per = (count + nsl - 1) / nsl;
+    if (threadIdx.x < nsl * kk2) {
+        const int e = threadIdx.x % kk2, sl = threadIdx.x / kk2;
+        const int b0 = sl * per, cnt = max(0, min(count, b0 + per) - b0);
+        sBuf[sl * kk2 + e] = sum_strided(src + (int64_t)b0 * kk2 + e, cnt, kk2);
+    }
+    __syncthreads();
+    if (threadIdx.x < kk2) {
+        double s2 = 0.0;
+        for (int sl = 0; sl < nsl; ++sl) s2 += sBuf[sl * kk2 + threadIdx.x];
+        dst[threadIdx.x] = s2;
+    }
+    __syncthreads();
+}
+
+template <int NI>
+__device__ __forceinline__ void gram_accumulate(const double* __restrict__ sT, int rows, int rows_per_tile, int k,
+                                                int ns, double (&gacc)[NI]) {
+    const int kk2 = k * k;
+    const int rps = (rows_per_tile + ns - 1) / ns;
+#pragma unroll
+    for (int q = 0; q < NI; ++q) {
+        const int item = threadIdx.x + q * kTailThreads;
+        if (item < kk2 * ns) {
+            const int pair = item % kk2, sl = item / kk2;
+            const int a = pair / k, b = pair - a * k;
+            const int rb = sl * rps, re = min(rows, rb + rps);
+            double s2 = gacc[q];
+            for (int r = rb; r < re; ++r) s2 = fma(sT[r * k + a], sT[r * k + b], s2);
+            gacc[q] = s2;
+        }
+    }
+}
+
+// Combine the slices through shared memory (sBuf: >= k*k*ns doubles) and write this block's k*k partial.
+template <int NI>
+__device__ __forceinline__ void gram_store(double* __restrict__ sBuf, int k, int ns, const double (&gacc)[NI],
+                                           double* __restrict__ part) {
+    const int kk2 = k * k;
+    if (ns == 1) {
+#pragma unroll
+        for (int q = 0; q < NI; ++q) {
+            const int item = threadIdx.x + q * kTailThreads;
+            if (item < kk2) part[item] = gacc[q];
+        }
+        return;
+    }
+    __syncthreads();
+    if (threadIdx.x < kk2 * ns) sBuf[threadIdx.x] = gacc[0];             // ns > 1 implies NI == 1
+    __syncthreads();
+    if (threadIdx.x < kk2) {
+        double s2 = 0.0;
+        for (int sl = 0; sl < ns; ++sl) s2 += sBuf[sl * kk2 + threadIdx.x];
+        part[threadIdx.x] = s2;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
 // U update (:421-422) + per-block partials of U^T U (:425).  sum(U^2) (:359) is its trace.
 //   A = sum of the pass-1 partials ; den = U.Gv + U ; U <- U * (A / den  if den != 0 else 1)
-// Persistent blocks loop over row tiles; the tile of new U rows is staged in shared memory and every
-// thread accumulates its (a,b) pairs of the Gram matrix in registers across tiles.
+// Blocks of 1024 threads loop over row tiles; the tile of new U rows is staged in shared memory.
 // ----------------------------------------------------------------------------------------------------
-constexpr int kMaxPairsPerThread = 64;   // k <= 128 with 256 threads
-
-template <int NQ>
-__global__ void __launch_bounds__(256)
+template <int NI>
+__global__ void __launch_bounds__(kTailThreads)
 u_update_kernel(double* __restrict__ U, const double* __restrict__ Apart, int achunks, const double* __restrict__ Gv,
                 int64_t m, int k, int rows_per_tile, double* __restrict__ Gu_part) {
     extern __shared__ double sm[];
     double* sGv = sm;                  // k*k
-    double* sU = sm + k * k;           // rows_per_tile * k   (new U rows)
+    double* sU = sm + k * k;           // max(rows_per_tile * k, 1024)   (new U rows; slice buffer at the end)
     const int kk2 = k * k;
+    const int ns = gram_slices(k);
     for (int i = threadIdx.x; i < kk2; i += blockDim.x) sGv[i] = Gv[i];
-    double gacc[NQ];
+    double gacc[NI];
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) gacc[q] = 0.0;
+    for (int q = 0; q < NI; ++q) gacc[q] = 0.0;
     __syncthreads();
     const int64_t ntiles = (m + rows_per_tile - 1) / rows_per_tile;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -166,23 +245,10 @@ u_update_kernel(double* __restrict__ U, const double* __restrict__ Apart, int ac
         }
         __syncthreads();
         for (int e = threadIdx.x; e < rows * k; e += blockDim.x) U[r0 * k + e] = sU[e];
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            const int pidx = threadIdx.x + q * 256;
-            if (pidx < kk2) {
-                const int a = pidx / k, b = pidx - a * k;
-                double s = gacc[q];
-                for (int r = 0; r < rows; ++r) s = fma(sU[r * k + a], sU[r * k + b], s);
-                gacc[q] = s;
-            }
-        }
+        gram_accumulate<NI>(sU, rows, rows_per_tile, k, ns, gacc);
         __syncthreads();
     }
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-        const int pidx = threadIdx.x + q * 256;
-        if (pidx < kk2) Gu_part[(int64_t)blockIdx.x * kk2 + pidx] = gacc[q];
-    }
+    gram_store<NI>(sU, k, ns, gacc, Gu_part + (int64_t)blockIdx.x * kk2);
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -617,31 +683,131 @@ __global__ void build_active_kernel(Pathways pw, const int32_t* __restrict__ act
 }
 
 // ----------------------------------------------------------------------------------------------------
-// V update (:425-444) + per-block partials of V_new^T V_new and sum(V_new * B).
+// Objective of one inner step (:336-372) without a pass over X, and the tradeoff feedback (:542-548).
+//   recon^2 = ||X||^2 - 2 sum(V_new*B) + sum(Gu*Gv_new)        (B = X^T U_new, Gu = U_new^T U_new)
+//   manifold = sum_k vhat_k^T Lhat_{p_k} vhat_k ; ignore = sum_k sum_{i in supp} 1/(vhat_i + 1)
+//   fro = trace(Gu) = sum(U^2)
+// Executed by ONE block of 1024 threads (the last block of the V update to finish); every phase is one
+// round of independent loads followed by a fixed-order reduction.  Publishes Gv_new = V_new^T V_new for
+// the next step's U update.  Loads bypass L1 (__ldcg): the data was just written by other SMs.
+// ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void objective_block(const double* __restrict__ V, int k, const double* __restrict__ sGu,
+                                                double* __restrict__ sGv, double* __restrict__ sSl,
+                                                double* __restrict__ scratch, const double* __restrict__ Gv_part,
+                                                const double* __restrict__ VB_part, int vblocks,
+                                                const double* __restrict__ normX_sq, const ActiveSet& as,
+                                                double* __restrict__ Gv, double* __restrict__ gd, double tradeoff,
+                                                double* __restrict__ obj_out, int* __restrict__ step_counter,
+                                                int obj_capacity) {
+    const int kk2 = k * k;
+    const int t = threadIdx.x;
+    if (kk2 <= 1024) {
+        const int nsl = 1024 / kk2;
+        const int per = (vblocks + nsl - 1) / nsl;
+        if (t < nsl * kk2) {
+            const int e = t % kk2, sl = t / kk2;
+            const int b0 = sl * per, cnt = max(0, min(vblocks, b0 + per) - b0);
+            double s2 = 0.0;
+            for (int b = 0; b < cnt; ++b) s2 += __ldcg(Gv_part + (int64_t)(b0 + b) * kk2 + e);
+            sSl[sl * kk2 + e] = s2;
+        }
+        __syncthreads();
+        if (t < kk2) {
+            double s2 = 0.0;
+            for (int sl = 0; sl < nsl; ++sl) s2 += sSl[sl * kk2 + t];
+            sGv[t] = s2;
+            Gv[t] = s2;
+        }
+    } else {
+        for (int e = t; e < kk2; e += blockDim.x) {
+            double s2 = 0.0;
+            for (int b = 0; b < vblocks; ++b) s2 += __ldcg(Gv_part + (int64_t)b * kk2 + e);
+            sGv[e] = s2;
+            Gv[e] = s2;
+        }
+    }
+    __syncthreads();
+    double gg = 0.0, fr = 0.0;
+    for (int e = t; e < kk2; e += blockDim.x) {
+        const double gu = sGu[e];
+        gg = fma(sGv[e], gu, gg);
+        if (e / k == e % k) fr += gu;                                                       // :359
+    }
+    double vb = 0.0;
+    for (int b = t; b < vblocks; b += blockDim.x) vb += __ldcg(VB_part + b);
+    double man = 0.0, ign = 0.0;
+    for (int64_t i = t; i < as.n_diag; i += blockDim.x) {
+        const int c = as.diag_factor[i];
+        const double vr = __ldcg(V + (int64_t)as.diag_gene[i] * k + c) / sqrt(sGv[c * k + c]);   // :345
+        man = fma(as.diag_coef[i] * vr, vr, man);
+        ign += 1.0 / (vr + 1.0);                                                            // :352
+    }
+    for (int64_t i = t; i < as.n_off; i += blockDim.x) {
+        const int c = as.off_factor[i];
+        const double nrm = sqrt(sGv[c * k + c]);
+        const double vr = __ldcg(V + (int64_t)as.off_r[i] * k + c) / nrm;
+        const double vc = __ldcg(V + (int64_t)as.off_c[i] * k + c) / nrm;
+        man = fma(as.off_coef[i] * vc, vr, man);                                            // :350
+    }
+    const double GG = block_sum(gg, scratch);
+    const double FRO = block_sum(fr, scratch);
+    const double VB = block_sum(vb, scratch);
+    const double MAN = block_sum(man, scratch);
+    const double IGN = block_sum(ign, scratch);
+    if (t == 0) {
+        const double gamma = gd[0], delta = gd[1];
+        const double r2 = normX_sq[0] - 2.0 * VB + GG;
+        const double recon = sqrt(r2 > 0.0 ? r2 : 0.0);
+        const double obj = recon + gamma * MAN + delta * IGN + FRO;                         // :362
+        const int s2 = *step_counter;
+        if (s2 < obj_capacity) {
+            double* o = obj_out + (int64_t)s2 * kObjStride;
+            o[0] = recon; o[1] = MAN; o[2] = IGN; o[3] = FRO; o[4] = obj; o[5] = gamma; o[6] = delta; o[7] = r2;
+        }
+        *step_counter = s2 + 1;
+        if (tradeoff >= 0.0) {                                                              // :542-548
+            const double den = tradeoff * MAN;
+            const double g2 = (den == 0.0) ? 1.0 : ((1.0 - tradeoff) * recon) / den;
+            gd[0] = g2; gd[1] = g2;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// V update (:425-444) fused with the objective (:336-372).
+//   B  = fixed-order sum of `bchunks` partials (the pass-2 partials directly on one GPU; the all-reduced
+//        packed buffer with bchunks = 1 when sharded), Gu likewise from `gchunks` partials
 //   C = V.Gu ; num = B + (gamma*W v + delta*(v+1)^-2 on the support) ; den = C + gamma*deg*v
 //   den < eps -> eps ; V <- V*num/den ; V < eps -> eps
-// red = [B | Gu | .] (after the all-reduce).  gd = {gamma, delta} on the device.  V is double-buffered:
-// pathway neighbours of a gene may be updated by another block, so new values go to Vnew while every
-// block reads the untouched Vold.
+// V is double-buffered: pathway neighbours of a gene may be updated by another block, so new values go to Vnew
+// while every block reads the untouched Vold.  Every block leaves partials of V_new^T V_new and
+// sum(V_new * B); the last block to finish (atomic ticket) evaluates the objective from them.
 // ----------------------------------------------------------------------------------------------------
-template <int NQ>
-__global__ void __launch_bounds__(256)
-v_update_kernel(const double* __restrict__ Vold, double* __restrict__ Vnew, const double* __restrict__ red,
-                int n, int k, Pathways pw, const int32_t* __restrict__ active, const int32_t* __restrict__ pos,
-                const double* __restrict__ gd, int rows_per_tile, double* __restrict__ Gv_part,
-                double* __restrict__ VB_part) {
+template <int NI>
+__global__ void __launch_bounds__(kTailThreads)
+v_update_objective_kernel(const double* __restrict__ Vold, double* __restrict__ Vnew,
+                          const double* __restrict__ Bsrc, int bchunks, int64_t bstride,
+                          const double* __restrict__ Gusrc, int gchunks, int n, int k, Pathways pw,
+                          const int32_t* __restrict__ active, const int32_t* __restrict__ pos,
+                          double* __restrict__ gd, int rows_per_tile, double* __restrict__ Gv_part,
+                          double* __restrict__ VB_part, const double* __restrict__ normX_sq, ActiveSet as,
+                          double* __restrict__ Gv, double tradeoff, double* __restrict__ obj_out,
+                          int* __restrict__ step_counter, int obj_capacity, unsigned int* __restrict__ ticket) {
     extern __shared__ double sm[];
     double* sGu = sm;                   // k*k
-    double* sV = sm + k * k;            // rows_per_tile*k (new V rows)
+    double* sGv = sm + k * k;           // k*k   (objective)
+    // Two k*k arrays do not fit for k > 64 (2 x 128 KB at k = 128): then the objective keeps Gv_new in global
+    // memory and the second slot shrinks to the 1024-double slice buffer (the host sizes smem the same way).
+    double* sV = sm + k * k + (k > 64 ? 1024 : k * k);   // max(rows_per_tile*k, 1024): new V rows / slice sums
     __shared__ double scratch[32];
+    __shared__ int s_last;
     const int kk2 = k * k;
-    const int64_t nk = (int64_t)n * k;
-    const double* B = red;
-    for (int i = threadIdx.x; i < kk2; i += blockDim.x) sGu[i] = red[nk + i];
+    const int ns = gram_slices(k);
+    sum_gram_partials(sGu, Gusrc, gchunks, kk2, sV);
     const double gamma = gd[0], delta = gd[1];
-    double gacc[NQ];
+    double gacc[NI];
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) gacc[q] = 0.0;
+    for (int q = 0; q < NI; ++q) gacc[q] = 0.0;
     double vb = 0.0;
     __syncthreads();
     const int ntiles = (n + rows_per_tile - 1) / rows_per_tile;
@@ -652,10 +818,10 @@ v_update_kernel(const double* __restrict__ Vold, double* __restrict__ Vnew, cons
             const int r = e / k, c = e - r * k;
             const int j = j0 + r;
             const double* vrow = Vold + (int64_t)j * k;
+            const double b = sum_strided(Bsrc + (int64_t)j * k + c, bchunks, bstride);   // X^T U  (:424)
             double cden = 0.0;
-            for (int l = 0; l < k; ++l) cden = fma(vrow[l], sGu[l * k + c], cden);   // V.Gu   (:425)
+            for (int l = 0; l < k; ++l) cden = fma(vrow[l], sGu[l * k + c], cden);       // V.Gu   (:425)
             const double v = vrow[c];
-            const double b = B[(int64_t)j * k + c];
             double num = b, den = cden;
             const int32_t pr = pos[(int64_t)j * k + c];
             if (pr >= 0) {
@@ -677,25 +843,25 @@ v_update_kernel(const double* __restrict__ Vold, double* __restrict__ Vnew, cons
             vb = fma(vn, b, vb);
         }
         __syncthreads();
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            const int pidx = threadIdx.x + q * 256;
-            if (pidx < kk2) {
-                const int a = pidx / k, b2 = pidx - a * k;
-                double s = gacc[q];
-                for (int r = 0; r < rows; ++r) s = fma(sV[r * k + a], sV[r * k + b2], s);
-                gacc[q] = s;
-            }
-        }
+        gram_accumulate<NI>(sV, rows, rows_per_tile, k, ns, gacc);
         __syncthreads();
     }
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-        const int pidx = threadIdx.x + q * 256;
-        if (pidx < kk2) Gv_part[(int64_t)blockIdx.x * kk2 + pidx] = gacc[q];
+    gram_store<NI>(sV, k, ns, gacc, Gv_part + (int64_t)blockIdx.x * kk2);
+    const double tvb = block_sum(vb, scratch);
+    if (threadIdx.x == 0) VB_part[blockIdx.x] = tvb;
+    // ---- last block done: objective ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int tk = atomicAdd(ticket, 1u);
+        s_last = (tk == gridDim.x - 1) ? 1 : 0;
     }
-    const double t = block_sum(vb, scratch);
-    if (threadIdx.x == 0) VB_part[blockIdx.x] = t;
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) *ticket = 0u;                 // re-arm for the next launch
+    __threadfence();
+    objective_block(Vnew, k, sGu, k > 64 ? Gv : sGv, k > 64 ? sGv : sV, scratch, Gv_part, VB_part, (int)gridDim.x, normX_sq,
+                    as, Gv, gd, tradeoff, obj_out, step_counter, obj_capacity);
 }
 
 // Gram of V from scratch (after prmf_set_UV): same tiling as the update kernel so partial layout matches.
@@ -742,98 +908,6 @@ sum_gram_parts_kernel(const double* __restrict__ G_part, int blocks, int kk2, do
         double s = 0.0;
         for (int b = 0; b < blocks; ++b) s += G_part[(int64_t)b * kk2 + e];
         G[e] = s;
-    }
-}
-
-// ----------------------------------------------------------------------------------------------------
-// Objective of one inner step (:336-372) without a pass over X, and the tradeoff feedback (:542-548).
-//   recon^2 = ||X||^2 - 2 sum(V_new*B) + sum(Gu*Gv_new)        (B = X^T U_new, Gu = U_new^T U_new)
-//   manifold = sum_k vhat_k^T Lhat_{p_k} vhat_k ; ignore = sum_k sum_{i in supp} 1/(vhat_i + 1)
-//   fro = trace(Gu) = sum(U^2)
-// One block of 1024 threads; every phase is one round of independent loads followed by a fixed-order
-// reduction.  Also publishes Gv_new = V_new^T V_new for the next step's U update.
-// ----------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-objective_kernel(const double* __restrict__ V, int n, int k, const double* __restrict__ red,
-                 const double* __restrict__ Gv_part, const double* __restrict__ VB_part, int vblocks,
-                 const double* __restrict__ normX_sq, ActiveSet as, double* __restrict__ Gv,
-                 double* __restrict__ gd, double tradeoff, double* __restrict__ obj_out,
-                 int* __restrict__ step_counter, int obj_capacity) {
-    extern __shared__ double sm[];
-    double* sGv = sm;                 // k*k
-    double* sSl = sm + k * k;         // <= 1024 slice sums
-    __shared__ double scratch[32];
-    const int kk2 = k * k;
-    const int64_t nk = (int64_t)n * k;
-    const int t = threadIdx.x;
-    // Gv_new[e] = sum over the V-update blocks' partials, in block order (slices, then slice sums in order)
-    if (kk2 <= 1024) {
-        const int nsl = 1024 / kk2;
-        const int per = (vblocks + nsl - 1) / nsl;
-        if (t < nsl * kk2) {
-            const int e = t % kk2, sl = t / kk2;
-            const int b0 = sl * per, cnt = max(0, min(vblocks, b0 + per) - b0);
-            sSl[sl * kk2 + e] = sum_strided(Gv_part + (int64_t)b0 * kk2 + e, cnt, kk2);
-        }
-        __syncthreads();
-        if (t < kk2) {
-            double s = 0.0;
-            for (int sl = 0; sl < nsl; ++sl) s += sSl[sl * kk2 + t];
-            sGv[t] = s;
-            Gv[t] = s;
-        }
-    } else {
-        for (int e = t; e < kk2; e += blockDim.x) {
-            const double s = sum_strided(Gv_part + e, vblocks, kk2);
-            sGv[e] = s;
-            Gv[e] = s;
-        }
-    }
-    __syncthreads();
-    double gg = 0.0, fr = 0.0;
-    for (int e = t; e < kk2; e += blockDim.x) {
-        const double gu = red[nk + e];
-        gg = fma(sGv[e], gu, gg);
-        if (e / k == e % k) fr += gu;                                                       // :359
-    }
-    double vb = 0.0;
-    for (int b = t; b < vblocks; b += blockDim.x) vb += VB_part[b];
-    // manifold / ignore over the flattened normalised Laplacians of the active pathways
-    double man = 0.0, ign = 0.0;
-    for (int64_t i = t; i < as.n_diag; i += blockDim.x) {
-        const int c = as.diag_factor[i];
-        const double vr = V[(int64_t)as.diag_gene[i] * k + c] / sqrt(sGv[c * k + c]);       // :345
-        man = fma(as.diag_coef[i] * vr, vr, man);
-        ign += 1.0 / (vr + 1.0);                                                            // :352
-    }
-    for (int64_t i = t; i < as.n_off; i += blockDim.x) {
-        const int c = as.off_factor[i];
-        const double nrm = sqrt(sGv[c * k + c]);
-        const double vr = V[(int64_t)as.off_r[i] * k + c] / nrm;
-        const double vc = V[(int64_t)as.off_c[i] * k + c] / nrm;
-        man = fma(as.off_coef[i] * vc, vr, man);                                            // :350
-    }
-    const double GG = block_sum(gg, scratch);
-    const double FRO = block_sum(fr, scratch);
-    const double VB = block_sum(vb, scratch);
-    const double MAN = block_sum(man, scratch);
-    const double IGN = block_sum(ign, scratch);
-    if (t == 0) {
-        const double gamma = gd[0], delta = gd[1];
-        const double r2 = normX_sq[0] - 2.0 * VB + GG;
-        const double recon = sqrt(r2 > 0.0 ? r2 : 0.0);
-        const double obj = recon + gamma * MAN + delta * IGN + FRO;                         // :362
-        const int s = *step_counter;
-        if (s < obj_capacity) {
-            double* o = obj_out + (int64_t)s * kObjStride;
-            o[0] = recon; o[1] = MAN; o[2] = IGN; o[3] = FRO; o[4] = obj; o[5] = gamma; o[6] = delta; o[7] = r2;
-        }
-        *step_counter = s + 1;
-        if (tradeoff >= 0.0) {                                                              // :542-548
-            const double den = tradeoff * MAN;
-            const double g2 = (den == 0.0) ? 1.0 : ((1.0 - tradeoff) * recon) / den;
-            gd[0] = g2; gd[1] = g2;
-        }
     }
 }
 

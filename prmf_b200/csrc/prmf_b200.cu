@@ -84,7 +84,8 @@ struct prmf_handle {
     int64_t rows_per_chunk1 = 0;
     int panels = 0, panel_w = 0, chunks = 0;         // pass 2: panels over genes, chunks over samples
     int64_t rows_per_chunk = 0;
-    int ktile = 0, nq = 1;
+    int ktile = 0, nq = 1, ni = 1;
+    unsigned int* ticket = nullptr;
     // TMA (bulk-async) variant of the X-stream kernel: used when one factor tile covers k
     bool use_tma = false;
     int tma_fg = 1, tma_kt = 0;               // factor groups / factors per thread of the general-k kernel
@@ -302,27 +303,55 @@ int launch_xtu(prmf_handle* h) {
         default: { constexpr int NQ = 64; EXPR; } break; \
     }
 
-size_t uu_smem(const prmf_handle* h) { return sizeof(double) * ((size_t)h->k * h->k + (size_t)h->uu_rows * h->k); }
-size_t vu_smem(const prmf_handle* h) { return sizeof(double) * ((size_t)h->k * h->k + (size_t)h->vu_rows * h->k); }
+#define NI_SWITCH(ni, EXPR)                    \
+    switch (ni) {                              \
+        case 1: { constexpr int NI = 1; EXPR; } break;   \
+        case 2: { constexpr int NI = 2; EXPR; } break;   \
+        case 4: { constexpr int NI = 4; EXPR; } break;   \
+        case 8: { constexpr int NI = 8; EXPR; } break;   \
+        default: { constexpr int NI = 16; EXPR; } break; \
+    }
+
+int pick_ni(int k) {
+    const int items = k * k * gram_slices(k);
+    const int need = (items + kTailThreads - 1) / kTailThreads;
+    return need <= 1 ? 1 : need <= 2 ? 2 : need <= 4 ? 4 : need <= 8 ? 8 : 16;
+}
+
+size_t uu_smem(const prmf_handle* h) {
+    return sizeof(double) * ((size_t)h->k * h->k + std::max<size_t>((size_t)h->uu_rows * h->k, 1024));
+}
+size_t vu_smem(const prmf_handle* h) {
+    const size_t kk2 = (size_t)h->k * h->k;
+    // sGu + (sGv when k <= 64; for larger k that slot only holds the 1024-double slice buffer) + V tile
+    return sizeof(double) * (kk2 + (h->k > 64 ? 1024 : kk2) + std::max<size_t>((size_t)h->vu_rows * h->k, 1024));
+}
 size_t gram_smem(const prmf_handle* h) { return sizeof(double) * ((size_t)h->vu_rows * h->k); }
-size_t obj_smem(const prmf_handle* h) { return sizeof(double) * ((size_t)h->k * h->k + 1024); }
 
 int launch_u_update(prmf_handle* h) {
     if (h->m == 0) {
         CU(cudaMemsetAsync(h->Gu_part, 0, sizeof(double) * h->uu_grid * h->k * h->k, h->stream));
         return PRMF_OK;
     }
-    NQ_SWITCH(h->nq, (u_update_kernel<NQ><<<h->uu_grid, 256, uu_smem(h), h->stream>>>(
+    NI_SWITCH(h->ni, (u_update_kernel<NI><<<h->uu_grid, kTailThreads, uu_smem(h), h->stream>>>(
                          h->U, h->Apart, h->use_tma ? h->tchunks1 : h->chunks1, h->Gv, h->m, h->k, h->uu_rows, h->Gu_part)));
     LAUNCH_CHECK("u_update_kernel");
     return PRMF_OK;
 }
 
-int launch_v_update(prmf_handle* h) {
-    NQ_SWITCH(h->nq, (v_update_kernel<NQ><<<h->vu_grid, 256, vu_smem(h), h->stream>>>(
-                         h->Vbuf[h->vcur], h->Vbuf[h->vcur ^ 1], h->red, (int)h->n, h->k, h->pw, h->active, h->pos,
-                         h->gd, h->vu_rows, h->Gv_part, h->VB_part)));
-    LAUNCH_CHECK("v_update_kernel");
+// V update + objective.  `sharded`: B and Gu come from the all-reduced packed buffer, else straight from
+// the pass-2 / U-update partials (the fixed-order sums happen inside the kernel).
+int launch_v_update_objective(prmf_handle* h, bool sharded, double tradeoff) {
+    const int64_t nk = h->n * h->k;
+    const double* Bsrc = sharded ? h->red : h->Bpart;
+    const int bchunks = sharded ? 1 : (h->use_tma ? h->tchunks : h->chunks);
+    const double* Gusrc = sharded ? h->red + nk : h->Gu_part;
+    const int gchunks = sharded ? 1 : h->uu_grid;
+    NI_SWITCH(h->ni, (v_update_objective_kernel<NI><<<h->vu_grid, kTailThreads, vu_smem(h), h->stream>>>(
+                         h->Vbuf[h->vcur], h->Vbuf[h->vcur ^ 1], Bsrc, bchunks, nk, Gusrc, gchunks, (int)h->n, h->k, h->pw,
+                         h->active, h->pos, h->gd, h->vu_rows, h->Gv_part, h->VB_part, h->normX_sq, h->as, h->Gv,
+                         tradeoff, h->obj, h->step_counter, h->obj_capacity, h->ticket)));
+    LAUNCH_CHECK("v_update_objective_kernel");
     h->vcur ^= 1;
     return PRMF_OK;
 }
@@ -456,22 +485,18 @@ int enqueue_steps(prmf_handle* h, int n_steps, double gamma, double delta, doubl
         if (rc) return rc;
         tic(2); rc = launch_xtu(h); toc();
         if (rc) return rc;
-        tic(3);
-        reduce_pack_kernel<<<(unsigned)((nk + kk2 + 2 + 255) / 256), 256, 0, h->stream>>>(
-            h->Bpart, h->use_tma ? h->tchunks : h->chunks, nk, h->Gu_part, h->uu_grid, h->k, h->red);
-        LAUNCH_CHECK("reduce_pack_kernel");
-        rc = allreduce(h, h->red, red_count);
-        toc();
+        const bool sharded = h->comm != nullptr;
+        if (sharded) {
+            tic(3);
+            reduce_pack_kernel<<<(unsigned)((nk + kk2 + 2 + 255) / 256), 256, 0, h->stream>>>(
+                h->Bpart, h->use_tma ? h->tchunks : h->chunks, nk, h->Gu_part, h->uu_grid, h->k, h->red);
+            LAUNCH_CHECK("reduce_pack_kernel");
+            rc = allreduce(h, h->red, red_count);
+            toc();
+            if (rc) return rc;
+        }
+        tic(4); rc = launch_v_update_objective(h, sharded, tradeoff); toc();
         if (rc) return rc;
-        tic(4); rc = launch_v_update(h); toc();
-        if (rc) return rc;
-        tic(5);
-        objective_kernel<<<1, 1024, obj_smem(h), h->stream>>>(h->Vbuf[h->vcur], (int)h->n, h->k, h->red, h->Gv_part,
-                                                              h->VB_part, h->vu_grid, h->normX_sq, h->as,
-                                                              h->Gv, h->gd, tradeoff, h->obj, h->step_counter,
-                                                              h->obj_capacity);
-        LAUNCH_CHECK("objective_kernel");
-        toc();
     }
     return PRMF_OK;
 }
@@ -558,10 +583,11 @@ int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global
     // launch geometry
     h->ktile = pick_ktile(k);
     h->nq = pick_nq(k);
-    h->uu_rows = (int)std::max<int64_t>(8, std::min<int64_t>(128, 4096 / k));
-    h->uu_grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count * 2, (m_local + h->uu_rows - 1) / h->uu_rows));
-    h->vu_rows = (int)std::max<int64_t>(8, std::min<int64_t>(32, 4096 / k));
-    h->vu_grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count * 2, (n + h->vu_rows - 1) / h->vu_rows));
+    h->ni = pick_ni(k);
+    h->uu_rows = (int)std::max<int64_t>(8, std::min<int64_t>(128, 2048 / k));
+    h->uu_grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (m_local + h->uu_rows - 1) / h->uu_rows));
+    h->vu_rows = (int)std::max<int64_t>(8, std::min<int64_t>(128, 2048 / k));
+    h->vu_grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (n + h->vu_rows - 1) / h->vu_rows));
     // pass 2 (X^T.U): column panels over genes, row chunks over samples
     h->panels = (int)((n + 1023) / 1024);
     h->panel_w = (int)round_up((n + h->panels - 1) / h->panels, 4);
@@ -627,11 +653,13 @@ int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global
     ALLOC(h->scal_part, (size_t)h->sm_count * 8);
     ALLOC(h->gd, 2);
     ALLOC(h->step_counter, 1);
+    ALLOC(h->ticket, 1);
     ALLOC(h->active, k);
     ALLOC(h->pos, nk);
 #undef ALLOC
     if (!rc) {
         cudaMemsetAsync(h->Xt, 0, sizeof(double) * n * h->ldxt, h->stream);
+        cudaMemsetAsync(h->ticket, 0, sizeof(unsigned int), h->stream);
         cudaMemsetAsync(h->U, 0, sizeof(double) * (m_local + pad_rows) * k, h->stream);
         cudaMemsetAsync(h->Vbuf[0], 0, sizeof(double) * (n + pad_rows) * k, h->stream);
         cudaMemsetAsync(h->Vbuf[1], 0, sizeof(double) * (n + pad_rows) * k, h->stream);
@@ -643,11 +671,12 @@ int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global
     // opt in to large dynamic shared memory where k needs it
     if (!rc) {
         NQ_SWITCH(h->nq, {
-            if (!rc) rc = set_smem(h, u_update_kernel<NQ>, uu_smem(h));
-            if (!rc) rc = set_smem(h, v_update_kernel<NQ>, vu_smem(h));
             if (!rc) rc = set_smem(h, gram_rows_kernel<NQ>, gram_smem(h));
         });
-        if (!rc) rc = set_smem(h, objective_kernel, obj_smem(h));
+        NI_SWITCH(h->ni, {
+            if (!rc) rc = set_smem(h, u_update_kernel<NI>, uu_smem(h));
+            if (!rc) rc = set_smem(h, v_update_objective_kernel<NI>, vu_smem(h));
+        });
     }
     if (rc) {
         g_create_error = h->err;
@@ -666,7 +695,7 @@ int prmf_destroy(prmf_handle* h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     void* bufs[] = {h->X, h->Xt, h->U, h->Vbuf[0], h->Vbuf[1], h->Ub, h->Vb, h->Gvb, h->Apart, h->Gv, h->Gu_part,
                     h->Gv_part, h->VB_part, h->Bpart, h->red, h->normX_sq, h->scal_part, h->gd, h->obj,
-                    h->step_counter, h->active, h->pos, h->scores_buf, h->as_i32, h->as_f64, h->as_off};
+                    h->step_counter, h->active, h->pos, h->scores_buf, h->as_i32, h->as_f64, h->as_off, h->ticket};
     for (void* b : bufs) if (b) cudaFree(b);
     for (void* b : h->pw_allocs) cudaFree(b);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);

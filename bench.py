@@ -212,7 +212,7 @@ def run_ours(a):
     import torch
     from prmf_b200 import CudaEngine
     from prmf_b200.dist import DistContext, row_block
-    from prmf_b200.engine import nccl_load, nccl_unique_id
+    from prmf_b200.engine import attach_collectives
     from prmf_b200.solver import init_latent_to_pathway_data, restrict_from_tables, sample_active
 
     if not torch.cuda.is_available():
@@ -233,10 +233,7 @@ def run_ours(a):
     gen.manual_seed(1234 + ctx.rank)
     Xd = torch.rand((m_local, a.n), dtype=torch.float64, device="cuda", generator=gen)
     eng = CudaEngine(m_local, a.m, a.n, a.k, device=dev, stream=stream.cuda_stream)
-    if ctx.world > 1:
-        nccl_load()
-        uid = ctx.broadcast_bytes(nccl_unique_id() if ctx.rank == 0 else None)
-        eng.attach_comm(ctx.rank, ctx.world, uid)
+    attach_collectives(eng, ctx)
     eng.set_X(Xd)
     eng.set_pathways(packed)
     normX = float(np.sqrt(eng.normX_sq))
@@ -393,6 +390,7 @@ def run_ours(a):
                "sample": "%d inner steps + 1 restrict of the numpy/scipy oracle at full shape, extrapolated to 10 + 1"
                          % a.cpu_inner_steps, **detail}
 
+    ctx.barrier()
     eng.close()
     if ctx.rank == 0:
         line = {
@@ -400,7 +398,10 @@ def run_ours(a):
             "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a), "step": "1 outer iteration = 10 inner steps + scores/restrict",
-                       "parallelism": "rows of X,U sharded over %d GPU(s)" % a.gpus,
+                       "parallelism": "rows of X,U sharded over %d GPU(s)" % a.gpus + (
+                           "" if a.gpus == 1 else (", per-step all-reduce of [X^T U | U^T U]: " + (
+                               "NCCL" if os.environ.get("PRMF_P2P", "1") == "0" else
+                               "fused into the V-update kernel over NVLink peer memory"))),
                        "l2": "inputs larger than L2 (X block %.2f GB per GPU per pass)" % (m_local * a.n * 8 / 1e9),
                        "inner_steps_per_s": 1000.0 / inner_ms},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),

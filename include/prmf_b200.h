@@ -120,6 +120,15 @@ int prmf_nccl_load(const char* libnccl_path);
 int prmf_comm_unique_id(uint8_t* id_out /* PRMF_UNIQUE_ID_BYTES */);
 int prmf_comm_init(prmf_handle* h, int rank, int nranks, const uint8_t* id);
 
+/* Optional: fuse the per-step all-reduce into the V-update kernel over NVLink peer memory (one-shot sum of
+ * all ranks' packed buffers with plain P2P loads, flag barrier in peer memory) instead of calling NCCL.
+ * Every rank exports a CUDA IPC handle of its exchange buffer (PRMF_IPC_HANDLE_BYTES), the handles are
+ * gathered by the host (any transport) and every rank attaches all of them.  Needs one process per GPU on
+ * one node with peer access; prmf_comm_init is still required (set-up reductions use NCCL). */
+#define PRMF_IPC_HANDLE_BYTES 64
+int prmf_p2p_export(prmf_handle* h, uint8_t* handle_out);
+int prmf_p2p_attach(prmf_handle* h, int rank, int nranks, const uint8_t* handles /* nranks x 64 bytes */);
+
 /* ---- introspection used by bench.py and the tests ---------------------------------------------------*/
 /* Number of kernel launches issued by this handle so far. */
 int64_t prmf_launch_count(const prmf_handle* h);

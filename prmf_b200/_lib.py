@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(HERE, "libprmf_b200.so")
 
 OBJ_STRIDE = 8
 UNIQUE_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 N_PHASES = 6
 PHASES = ("xv", "u_update", "xtu", "reduce", "v_update", "objective")
 
@@ -35,6 +36,8 @@ SYMBOLS = {
     "prmf_nccl_load": (c_int, [c_char_p]),
     "prmf_comm_unique_id": (c_int, [POINTER(c_uint8)]),
     "prmf_comm_init": (c_int, [_P, c_int, c_int, POINTER(c_uint8)]),
+    "prmf_p2p_export": (c_int, [_P, POINTER(c_uint8)]),
+    "prmf_p2p_attach": (c_int, [_P, c_int, c_int, POINTER(c_uint8)]),
     "prmf_launch_count": (c_int64, [_P]),
     "prmf_kernel_times": (c_int, [_P, c_int, POINTER(c_double), POINTER(c_int64)]),
     "prmf_set_profiling": (c_int, [_P, c_int]),

@@ -774,6 +774,56 @@ __device__ __forceinline__ void objective_block(const double* __restrict__ V, in
 }
 
 // ----------------------------------------------------------------------------------------------------
+// One-shot all-reduce over NVLink peer memory, fused into the V update (sample-sharded runs).
+// Every rank leaves its locally reduced packed buffer [X^T U | U^T U] in its own HBM; after a flag barrier
+// over peer memory every rank reads all ranks' buffers with plain P2P loads and adds them in rank order, so
+// all ranks obtain bitwise identical sums without a separate collective launch.  The packed buffers are
+// double-buffered by step parity: a rank can only write parity p again after it passed the barrier of the
+// step in between, which every peer reaches only after it finished reading parity p.
+// ----------------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 8;
+
+struct PeerExchange {
+    int nranks;                                // 0: no exchange (one GPU, or the NCCL path)
+    int rank;
+    const double* red[kMaxPeers];              // rank r's packed buffer of this step's parity (P2P mapped)
+    unsigned long long* flags[kMaxPeers];      // rank r's flag array: flags[r][q] = last step rank q announced
+    unsigned long long seq;                    // this step's sequence number (monotone)
+};
+
+__device__ __forceinline__ double ld_peer(const double* p) {
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+// Announce "my packed buffer of step seq is complete" to every rank, then wait until every rank has done so.
+__device__ __forceinline__ void peer_barrier(const PeerExchange& px) {
+    if (threadIdx.x < px.nranks) {
+        if (blockIdx.x == 0) {
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(px.flags[threadIdx.x] + px.rank), "l"(px.seq) : "memory");
+        }
+        const unsigned long long* mine = px.flags[px.rank] + threadIdx.x;
+        unsigned long long seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+        } while (seen < px.seq);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ double sum_peers(const PeerExchange& px, int64_t idx) {
+    double s = 0.0;
+    double t[kMaxPeers];
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r) t[r] = r < px.nranks ? ld_peer(px.red[r] + idx) : 0.0;
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r) s += t[r];
+    return s;
+}
+
+// ----------------------------------------------------------------------------------------------------
 // V update (:425-444) fused with the objective (:336-372).
 //   B  = fixed-order sum of `bchunks` partials (the pass-2 partials directly on one GPU; the all-reduced
 //        packed buffer with bchunks = 1 when sharded), Gu likewise from `gchunks` partials
@@ -792,7 +842,8 @@ v_update_objective_kernel(const double* __restrict__ Vold, double* __restrict__ 
                           double* __restrict__ gd, int rows_per_tile, double* __restrict__ Gv_part,
                           double* __restrict__ VB_part, const double* __restrict__ normX_sq, ActiveSet as,
                           double* __restrict__ Gv, double tradeoff, double* __restrict__ obj_out,
-                          int* __restrict__ step_counter, int obj_capacity, unsigned int* __restrict__ ticket) {
+                          int* __restrict__ step_counter, int obj_capacity, unsigned int* __restrict__ ticket,
+                          PeerExchange px) {
     extern __shared__ double sm[];
     double* sGu = sm;                   // k*k
     double* sGv = sm + k * k;           // k*k   (objective)
@@ -803,7 +854,14 @@ v_update_objective_kernel(const double* __restrict__ Vold, double* __restrict__ 
     __shared__ int s_last;
     const int kk2 = k * k;
     const int ns = gram_slices(k);
-    sum_gram_partials(sGu, Gusrc, gchunks, kk2, sV);
+    const int64_t nk_all = (int64_t)n * k;
+    if (px.nranks > 0) {
+        peer_barrier(px);
+        for (int i = threadIdx.x; i < kk2; i += blockDim.x) sGu[i] = sum_peers(px, nk_all + i);
+        __syncthreads();
+    } else {
+        sum_gram_partials(sGu, Gusrc, gchunks, kk2, sV);
+    }
     const double gamma = gd[0], delta = gd[1];
     double gacc[NI];
 #pragma unroll
@@ -818,7 +876,8 @@ v_update_objective_kernel(const double* __restrict__ Vold, double* __restrict__ 
             const int r = e / k, c = e - r * k;
             const int j = j0 + r;
             const double* vrow = Vold + (int64_t)j * k;
-            const double b = sum_strided(Bsrc + (int64_t)j * k + c, bchunks, bstride);   // X^T U  (:424)
+            const double b = px.nranks > 0 ? sum_peers(px, (int64_t)j * k + c)
+                                           : sum_strided(Bsrc + (int64_t)j * k + c, bchunks, bstride);   // X^T U  (:424)
             double cden = 0.0;
             for (int l = 0; l < k; ++l) cden = fma(vrow[l], sGu[l * k + c], cden);       // V.Gu   (:425)
             const double v = vrow[c];

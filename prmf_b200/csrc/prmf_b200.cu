@@ -97,6 +97,13 @@ struct prmf_handle {
     // multi-GPU
     NcclComm comm = nullptr;
     int rank = 0, nranks = 1;
+    // NVLink peer exchange (fused all-reduce): [red parity 0 | red parity 1 | flags]
+    double* p2p_buf = nullptr;
+    size_t p2p_red_count = 0;
+    bool p2p_ready = false;
+    void* peer_base[kMaxPeers] = {nullptr};
+    unsigned long long p2p_seq = 0;
+    int p2p_parity = 0;
 
     // introspection
     int64_t launches = 0;
@@ -343,6 +350,18 @@ int launch_u_update(prmf_handle* h) {
 // the pass-2 / U-update partials (the fixed-order sums happen inside the kernel).
 int launch_v_update_objective(prmf_handle* h, bool sharded, double tradeoff) {
     const int64_t nk = h->n * h->k;
+    PeerExchange px{};
+    if (sharded && h->p2p_ready) {
+        px.nranks = h->nranks;
+        px.rank = h->rank;
+        px.seq = ++h->p2p_seq;
+        for (int r = 0; r < h->nranks; ++r) {
+            double* base = (double*)h->peer_base[r];
+            px.red[r] = base + (size_t)h->p2p_parity * h->p2p_red_count;
+            px.flags[r] = (unsigned long long*)(base + 2 * h->p2p_red_count);
+        }
+        h->p2p_parity ^= 1;
+    }
     const double* Bsrc = sharded ? h->red : h->Bpart;
     const int bchunks = sharded ? 1 : (h->use_tma ? h->tchunks : h->chunks);
     const double* Gusrc = sharded ? h->red + nk : h->Gu_part;
@@ -350,7 +369,7 @@ int launch_v_update_objective(prmf_handle* h, bool sharded, double tradeoff) {
     NI_SWITCH(h->ni, (v_update_objective_kernel<NI><<<h->vu_grid, kTailThreads, vu_smem(h), h->stream>>>(
                          h->Vbuf[h->vcur], h->Vbuf[h->vcur ^ 1], Bsrc, bchunks, nk, Gusrc, gchunks, (int)h->n, h->k, h->pw,
                          h->active, h->pos, h->gd, h->vu_rows, h->Gv_part, h->VB_part, h->normX_sq, h->as, h->Gv,
-                         tradeoff, h->obj, h->step_counter, h->obj_capacity, h->ticket)));
+                         tradeoff, h->obj, h->step_counter, h->obj_capacity, h->ticket, px)));
     LAUNCH_CHECK("v_update_objective_kernel");
     h->vcur ^= 1;
     return PRMF_OK;
@@ -488,10 +507,11 @@ int enqueue_steps(prmf_handle* h, int n_steps, double gamma, double delta, doubl
         const bool sharded = h->comm != nullptr;
         if (sharded) {
             tic(3);
+            double* dst = h->p2p_ready ? h->p2p_buf + (size_t)h->p2p_parity * h->p2p_red_count : h->red;
             reduce_pack_kernel<<<(unsigned)((nk + kk2 + 2 + 255) / 256), 256, 0, h->stream>>>(
-                h->Bpart, h->use_tma ? h->tchunks : h->chunks, nk, h->Gu_part, h->uu_grid, h->k, h->red);
+                h->Bpart, h->use_tma ? h->tchunks : h->chunks, nk, h->Gu_part, h->uu_grid, h->k, dst);
             LAUNCH_CHECK("reduce_pack_kernel");
-            rc = allreduce(h, h->red, red_count);
+            if (!h->p2p_ready) rc = allreduce(h, h->red, red_count);      // else: summed inside the V update
             toc();
             if (rc) return rc;
         }
@@ -692,6 +712,10 @@ int prmf_destroy(prmf_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     harvest_events(h);
+    if (h->p2p_ready)
+        for (int r = 0; r < h->nranks; ++r)
+            if (r != h->rank && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
+    if (h->p2p_buf) cudaFree(h->p2p_buf);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     void* bufs[] = {h->X, h->Xt, h->U, h->Vbuf[0], h->Vbuf[1], h->Ub, h->Vb, h->Gvb, h->Apart, h->Gv, h->Gu_part,
                     h->Gv_part, h->VB_part, h->Bpart, h->red, h->normX_sq, h->scal_part, h->gd, h->obj,
@@ -956,6 +980,47 @@ int prmf_comm_init(prmf_handle* h, int rank, int nranks, const uint8_t* id) {
         return fail(h, PRMF_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
     }
     h->rank = rank; h->nranks = nranks;
+    return PRMF_OK;
+}
+
+int prmf_p2p_export(prmf_handle* h, uint8_t* handle_out) {
+    if (!h || !handle_out) return PRMF_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == PRMF_IPC_HANDLE_BYTES, "IPC handle size");
+    CU(cudaSetDevice(h->device));
+    if (!h->p2p_buf) {
+        h->p2p_red_count = (size_t)round_up(h->n * h->k + (int64_t)h->k * h->k + 2, 32);
+        const size_t total = 2 * h->p2p_red_count + 64;
+        int rc = dalloc(h, &h->p2p_buf, total);
+        if (rc) return rc;
+        CU(cudaMemset(h->p2p_buf, 0, total * sizeof(double)));
+    }
+    cudaIpcMemHandle_t hd;
+    CU(cudaIpcGetMemHandle(&hd, h->p2p_buf));
+    memcpy(handle_out, &hd, sizeof hd);
+    return PRMF_OK;
+}
+
+int prmf_p2p_attach(prmf_handle* h, int rank, int nranks, const uint8_t* handles) {
+    if (!h || !handles) return PRMF_ERR_ARG;
+    if (!h->p2p_buf) return fail(h, PRMF_ERR_STATE, "call prmf_p2p_export first");
+    if (nranks < 2 || nranks > kMaxPeers || rank < 0 || rank >= nranks)
+        return fail(h, PRMF_ERR_ARG, "prmf_p2p_attach: bad rank %d / %d (max %d ranks)", rank, nranks, kMaxPeers);
+    if (h->comm && (h->rank != rank || h->nranks != nranks))
+        return fail(h, PRMF_ERR_ARG, "prmf_p2p_attach: rank/nranks differ from prmf_comm_init");
+    CU(cudaSetDevice(h->device));
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) { h->peer_base[r] = h->p2p_buf; continue; }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, handles + (size_t)r * PRMF_IPC_HANDLE_BYTES, sizeof hd);
+        cudaError_t e = cudaIpcOpenMemHandle(&h->peer_base[r], hd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int q = 0; q < r; ++q)
+                if (q != rank && h->peer_base[q]) { cudaIpcCloseMemHandle(h->peer_base[q]); h->peer_base[q] = nullptr; }
+            return fail(h, PRMF_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+        }
+    }
+    h->rank = rank; h->nranks = nranks;
+    h->p2p_ready = true;
     return PRMF_OK;
 }
 

@@ -66,6 +66,15 @@ class DistContext:
         dist.broadcast_object_list(box, src=src)
         return box[0]
 
+    def all_gather_bytes(self, payload):
+        """Every rank's `payload` (bytes), in rank order."""
+        if self.world == 1:
+            return [payload]
+        import torch.distributed as dist
+        parts = [None] * self.world
+        dist.all_gather_object(parts, payload)
+        return parts
+
     def all_gather_rows(self, local, m_global):
         """Concatenate the ranks' row blocks (U at return, :778-792) in rank order."""
         if self.world == 1:

@@ -157,6 +157,17 @@ class CudaEngine:
         buf = (ctypes.c_uint8 * _lib.UNIQUE_ID_BYTES).from_buffer_copy(bytes(unique_id))
         self._ck(self.lib.prmf_comm_init(self.h, int(rank), int(nranks), buf))
 
+    def p2p_export(self):
+        buf = (ctypes.c_uint8 * _lib.IPC_HANDLE_BYTES)()
+        self._ck(self.lib.prmf_p2p_export(self.h, buf))
+        return bytes(buf)
+
+    def p2p_attach(self, rank, nranks, handles):
+        """handles: list of every rank's `p2p_export()` bytes, in rank order."""
+        blob = b"".join(handles)
+        buf = (ctypes.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self._ck(self.lib.prmf_p2p_attach(self.h, int(rank), int(nranks), buf))
+
     # -- introspection -------------------------------------------------------------------------------
     @property
     def launch_count(self):
@@ -204,3 +215,30 @@ def nccl_load():
     rc = lib.prmf_nccl_load(path.encode() if path else None)
     if rc != 0:
         raise _lib.PrmfLibraryError("prmf_nccl_load failed: %s" % lib.prmf_last_error(None).decode())
+
+
+def attach_collectives(eng, ctx, p2p=None):
+    """Give the engine of a multi-rank run its communicators: NCCL (set-up reductions, and the per-step
+    all-reduce when peer access is unavailable) and -- unless PRMF_P2P=0 -- the NVLink peer exchange that fuses
+    the per-step all-reduce into the V-update kernel.  Collective over `ctx`: call on every rank."""
+    import os
+    if ctx.world <= 1:
+        return eng
+    nccl_load()
+    uid = ctx.broadcast_bytes(nccl_unique_id() if ctx.rank == 0 else None, src=0)
+    eng.attach_comm(ctx.rank, ctx.world, uid)
+    if p2p is None:
+        p2p = os.environ.get("PRMF_P2P", "1") != "0"
+    if p2p and ctx.world <= 8:
+        handles = ctx.all_gather_bytes(eng.p2p_export())
+        ok = True
+        try:
+            eng.p2p_attach(ctx.rank, ctx.world, handles)
+        except _lib.PrmfLibraryError:
+            ok = False
+        # all ranks must agree, otherwise some would wait on flags nobody writes
+        flags = ctx.all_gather_bytes(b"1" if ok else b"0")
+        if not all(f == b"1" for f in flags):
+            raise _lib.PrmfLibraryError("NVLink peer exchange could not be set up on every rank; "
+                                        "rerun with PRMF_P2P=0 to use the NCCL all-reduce")
+    return eng

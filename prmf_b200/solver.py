@@ -18,7 +18,7 @@ import sys
 import numpy as np
 
 from .dist import DistContext, row_block
-from .engine import CudaEngine, nccl_load, nccl_unique_id
+from .engine import CudaEngine, attach_collectives
 from .pathways import PackedPathways, pack_pathways
 
 PERCENTILE = 19.9                              # prmf_runner.py:159
@@ -35,12 +35,7 @@ def default_engine_factory(m_local, m_global, n, k, ctx):
     """One CUDA engine per rank; with more than one rank the engines share an NCCL communicator."""
     device = ctx.local_rank if ctx.world > 1 else _current_device()
     eng = CudaEngine(m_local, m_global, n, k, device=device)
-    if ctx.world > 1:
-        nccl_load()
-        uid = nccl_unique_id() if ctx.rank == 0 else None
-        uid = ctx.broadcast_bytes(uid, src=0)
-        eng.attach_comm(ctx.rank, ctx.world, uid)
-    return eng
+    return attach_collectives(eng, ctx)
 
 
 def _current_device():
@@ -389,6 +384,7 @@ def nmf_pathway(X, Gs, gamma=1.0, delta=1.0, tradeoff=None, k_latent=6, tol=1e-3
             obj_data = best_obj_data
         U_local, V = eng.get_UV()
     finally:
+        ctx.barrier()          # peers may still be reading this rank's exchange buffer
         eng.close()
     U = ctx.all_gather_rows(U_local, m)
     obj_data = dict(obj_data)

@@ -142,6 +142,20 @@ int prmf_set_profiling(prmf_handle* h, int on);
 /* The cudaStream_t the handle launches on. */
 void* prmf_stream(const prmf_handle* h);
 
+/* ---- "next" row of the scope table: the step before the path --------------------------------------------
+ * GPU version of `X = quantile_transform(X)` (script/prmf_runner.py:1019-1020; sklearn defaults: uniform output,
+ * n_quantiles = min(1000, m), axis 0).  X_dev / out_dev are DEVICE pointers (m x n, row-major, leading dimensions
+ * ld / ld_out; out may alias X).  The caller supplies what numpy derives on the host so the device mirrors it
+ * exactly: references (np.linspace(0,1,nq)), and for q = (references*100)/100 the order-statistic indices
+ * lo = floor((ms-1) q), hi = min(lo+1, ms-1) and weights g = (ms-1) q - lo.  rows_dev (ms row indices, or NULL
+ * with ms == m) is sklearn's row subsample used for fitting the quantiles.  quantiles_out_host (n x nq,
+ * gene-major) may be NULL.  Fails on NaN input. */
+int prmf_quantile_transform(int device, void* stream, const double* X_dev, int64_t m, int64_t n, int64_t ld,
+                            const int64_t* rows_dev, int64_t ms, int nq, const double* refs_host,
+                            const int64_t* lo_host, const int64_t* hi_host, const double* g_host, double* out_dev,
+                            int64_t ld_out, double* quantiles_out_host);
+const char* prmf_preprocess_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,9 @@ SYMBOLS = {
     "prmf_kernel_times": (c_int, [_P, c_int, POINTER(c_double), POINTER(c_int64)]),
     "prmf_set_profiling": (c_int, [_P, c_int]),
     "prmf_stream": (_P, [_P]),
+    "prmf_quantile_transform": (c_int, [c_int, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, c_int, _P, _P, _P, _P, _P,
+                                        c_int64, _P]),
+    "prmf_preprocess_last_error": (c_char_p, []),
 }
 
 _lib = None

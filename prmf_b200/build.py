@@ -3,12 +3,19 @@ import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libprmf_b200.so")
-SOURCES = ["prmf_b200.cu"]
-HEADERS = ["kernels.cuh", "nccl_dyn.h", os.path.join("..", "..", "include", "prmf_b200.h")]
+HEADER = os.path.join(HERE, "..", "include", "prmf_b200.h")
+# translation unit -> headers it depends on
+SOURCES = {
+    "prmf_b200.cu": ["kernels.cuh", "nccl_dyn.h"],
+    "preprocess.cu": [],
+}
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
 def nvcc_path():
@@ -18,32 +25,62 @@ def nvcc_path():
     raise RuntimeError("nvcc not found; libprmf_b200.so cannot be built")
 
 
+def _mtime(path):
+    return os.path.getmtime(path) if os.path.exists(path) else 0.0
+
+
+def _obj(src):
+    return os.path.join(OBJDIR, os.path.splitext(src)[0] + ".o")
+
+
+def _stale_objects():
+    out = []
+    for src, deps in SOURCES.items():
+        newest = max([_mtime(os.path.join(CSRC, src)), _mtime(HEADER)] + [_mtime(os.path.join(CSRC, d)) for d in deps])
+        if _mtime(_obj(src)) < newest:
+            out.append(src)
+    return out
+
+
 def is_stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    for f in SOURCES + HEADERS:
-        p = os.path.join(CSRC, f)
-        if os.path.exists(p) and os.path.getmtime(p) > t:
-            return True
-    return False
+    for src, deps in SOURCES.items():
+        for f in [src] + deps:
+            if _mtime(os.path.join(CSRC, f)) > t:
+                return True
+    return _mtime(HEADER) > t
 
 
 def build_library(force=False, verbose=False):
-    """Compile the CUDA sources into prmf_b200/libprmf_b200.so.  Returns the path."""
+    """Compile the CUDA sources (one object per translation unit, rebuilt only when stale) and link
+    prmf_b200/libprmf_b200.so.  Returns the path."""
     if not force and not is_stale():
         return LIB
-    cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-Xcompiler", "-fPIC", "-shared", "-o", LIB]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    nvcc = nvcc_path()
+    os.makedirs(OBJDIR, exist_ok=True)
+    todo = list(SOURCES) if force else (_stale_objects() or [s for s in SOURCES if not os.path.exists(_obj(s))])
+
+    def compile_one(src):
+        cmd = [nvcc, "-O3", "-std=c++17"] + ARCH + ["-lineinfo", "-Xcompiler", "-fPIC", "-c", "-o", _obj(src),
+                                                     os.path.join(CSRC, src)]
+        if verbose:
+            cmd += ["-Xptxas", "-v"]
+        return src, subprocess.run(cmd, capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        for src, res in pool.map(compile_one, todo):
+            if res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+                raise RuntimeError("nvcc failed on %s" % src)
+            if verbose:
+                sys.stderr.write(res.stdout + res.stderr)
+    link = [nvcc, "-shared"] + ARCH + ["-o", LIB] + [_obj(s) for s in SOURCES] + ["-ldl"]
+    res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libprmf_b200.so")
-    if verbose:
-        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("linking libprmf_b200.so failed")
     return LIB
 
 

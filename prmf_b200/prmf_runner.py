@@ -236,11 +236,13 @@ def main(argv=None):
             break
 
     if not args.no_normalize:                                                    # :1019-1020
-        from sklearn.preprocessing import quantile_transform
-        X = quantile_transform(X)
+        # sklearn.preprocessing.quantile_transform(X) on the GPU; the result stays on the device for nmf_pathway
+        from .preprocess import quantile_transform
+        X = quantile_transform(np.asarray(X, dtype=np.float64), return_device=True)
 
     U_init = V_init = None                                                       # :1023-1064
     if args.manifolds_init is not None:
+        X_dev, X = X, (X.cpu().numpy() if hasattr(X, "is_cuda") else X)          # the NNLS seeding runs on the host
         Gs_init = [fp_to_G[fp] for fp in args.manifolds_init]
         if len(args.manifolds_init) < args.k_latent:
             non_init = list(set(manifold_fps) - set(args.manifolds_init))
@@ -269,6 +271,7 @@ def main(argv=None):
         sys.stdout.write("Using the following manifolds for initialization:\n{}\n".format("\n".join(init_fps)))
         with open(os.path.join(args.outdir, "init_pathways.txt"), "w") as fh:
             fh.write("\n".join(init_fps))
+        X = X_dev
 
     # :1067 -- like the reference only gamma, tradeoff, k_latent, U_init, V_init and verbose are forwarded
     U, V, obj_data = nmf_pathway(X, Gs, nodelist=nodelist, gamma=args.gamma, tradeoff=tradeoff,

@@ -111,6 +111,11 @@ int prmf_restore_best(prmf_handle* h);
  * used inside prmf_step; all-reduced when a communicator is attached). */
 int prmf_residual_sq(prmf_handle* h, double* out);
 
+/* Objective of the CURRENT X, U, V and active set as a standalone call (nmf_manifold_vec_obj, :336-372), with the
+ * residual taken by an explicit pass over X as the reference does.  out: PRMF_OBJ_STRIDE doubles, same layout as
+ * a row of prmf_step's obj_parts. */
+int prmf_objective(prmf_handle* h, double gamma, double delta, double* out);
+
 /* ---- multi-GPU (one handle per rank / process) ------------------------------------------------------
  * prmf_nccl_load dlopens the NCCL the host process already uses (path of libnccl.so.2, or NULL to look
  * it up); rank 0 calls prmf_comm_unique_id and ships the 128 bytes to the other ranks (any transport,

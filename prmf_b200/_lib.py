@@ -33,6 +33,7 @@ SYMBOLS = {
     "prmf_snapshot_best": (c_int, [_P]),
     "prmf_restore_best": (c_int, [_P]),
     "prmf_residual_sq": (c_int, [_P, POINTER(c_double)]),
+    "prmf_objective": (c_int, [_P, c_double, c_double, _P]),
     "prmf_nccl_load": (c_int, [c_char_p]),
     "prmf_comm_unique_id": (c_int, [POINTER(c_uint8)]),
     "prmf_comm_init": (c_int, [_P, c_int, c_int, POINTER(c_uint8)]),

@@ -1010,6 +1010,29 @@ scores_kernel(const double* __restrict__ V, int k, const double* __restrict__ Gv
     }
 }
 
+// manifold / ignore terms of the objective (:344-352) for the current V, standalone (prmf_objective).
+__global__ void __launch_bounds__(1024)
+manifold_ignore_kernel(const double* __restrict__ V, int k, const double* __restrict__ Gv, ActiveSet as,
+                       double* __restrict__ out2) {
+    __shared__ double scratch[32];
+    const int t = threadIdx.x;
+    double man = 0.0, ign = 0.0;
+    for (int64_t i = t; i < as.n_diag; i += blockDim.x) {
+        const int c = as.diag_factor[i];
+        const double vr = V[(int64_t)as.diag_gene[i] * k + c] / sqrt(Gv[c * k + c]);
+        man = fma(as.diag_coef[i] * vr, vr, man);
+        ign += 1.0 / (vr + 1.0);
+    }
+    for (int64_t i = t; i < as.n_off; i += blockDim.x) {
+        const int c = as.off_factor[i];
+        const double nrm = sqrt(Gv[c * k + c]);
+        man = fma(as.off_coef[i] * (V[(int64_t)as.off_c[i] * k + c] / nrm), V[(int64_t)as.off_r[i] * k + c] / nrm, man);
+    }
+    const double MAN = block_sum(man, scratch);
+    const double IGN = block_sum(ign, scratch);
+    if (t == 0) { out2[0] = MAN; out2[1] = IGN; }
+}
+
 // ----------------------------------------------------------------------------------------------------
 // Exact residual ||X - U V^T||_F^2 (verification only; one extra pass over X).  Warp per row.
 // ----------------------------------------------------------------------------------------------------

@@ -951,6 +951,44 @@ int prmf_residual_sq(prmf_handle* h, double* out) {
     return PRMF_OK;
 }
 
+int prmf_objective(prmf_handle* h, double gamma, double delta, double* out) {
+    if (!h || !out) return PRMF_ERR_ARG;
+    if (!h->have_X || !h->have_UV || !h->have_pw || !h->have_active)
+        return fail(h, PRMF_ERR_STATE, "prmf_objective needs X, U/V, pathways and the active set");
+    CU(cudaSetDevice(h->device));
+    int rc = ensure_pos(h);
+    if (rc) return rc;
+    double r2 = 0.0;
+    if ((rc = prmf_residual_sq(h, &r2))) return rc;                            // ||X - U V^T||^2, explicit pass (:337)
+    double* d = nullptr;
+    if ((rc = dalloc(h, &d, 4))) return rc;
+    const int blocks = h->sm_count * 4;
+    const int64_t mk = h->m * h->k;
+    if (mk > 0) {                                                              // sum(U^2) (:359); U is zero padded
+        sumsq_kernel<<<blocks, 256, 0, h->stream>>>(h->U, mk + 2, 1, (int)round_up(mk, 2), h->scal_part);
+        h->launches++;
+        sum_partials_kernel<<<1, 256, 0, h->stream>>>(h->scal_part, blocks, d + 2);
+        h->launches++;
+    } else {
+        cudaMemsetAsync(d + 2, 0, sizeof(double), h->stream);
+    }
+    rc = allreduce(h, d + 2, 1);
+    manifold_ignore_kernel<<<1, 1024, 0, h->stream>>>(h->Vbuf[h->vcur], h->k, h->Gv, h->as, d);
+    h->launches++;
+    double host[3] = {0, 0, 0};
+    cudaError_t e = cudaGetLastError();
+    if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(host, d, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(h, PRMF_ERR_CUDA, "prmf_objective: %s", cudaGetErrorString(e));
+    const double recon = std::sqrt(r2 > 0.0 ? r2 : 0.0);
+    out[0] = recon; out[1] = host[0]; out[2] = host[1]; out[3] = host[2];
+    out[4] = recon + gamma * host[0] + delta * host[1] + host[2];              // :362
+    out[5] = gamma; out[6] = delta; out[7] = r2;
+    return PRMF_OK;
+}
+
 int prmf_nccl_load(const char* libnccl_path) {
     const char* err = g_nccl.load(libnccl_path);
     if (err) return fail(nullptr, PRMF_ERR_NCCL, "%s", err);

@@ -152,6 +152,12 @@ class CudaEngine:
         self._ck(self.lib.prmf_residual_sq(self.h, ctypes.byref(out)))
         return out.value
 
+    def objective(self, gamma, delta):
+        """Objective parts of the current state (explicit residual pass); a row like `step`'s."""
+        out = np.empty(_lib.OBJ_STRIDE)
+        self._ck(self.lib.prmf_objective(self.h, float(gamma), float(delta), _ptr(out)))
+        return out
+
     # -- multi-GPU -----------------------------------------------------------------------------------
     def attach_comm(self, rank, nranks, unique_id):
         buf = (ctypes.c_uint8 * _lib.UNIQUE_ID_BYTES).from_buffer_copy(bytes(unique_id))

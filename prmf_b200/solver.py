@@ -215,6 +215,26 @@ def nmf_manifold_vec_update(X, U, V, pathways, active, n_steps=10, gamma=1.0, de
     return U2, V2, obj_data
 
 
+def nmf_manifold_vec_obj(X, U, V, pathways, active, gamma=1, delta=1, nodelist=None, engine=None):
+    """Objective parts for host arrays (:336-372): {'recon','manifold','ignore','fro','gamma','delta','obj'}.
+    recon is taken by an explicit pass over X, as the reference does."""
+    X = np.asarray(X)
+    m, n = X.shape
+    k = V.shape[1]
+    own = engine is None
+    eng = engine or CudaEngine(m, m, n, k, device=_current_device())
+    try:
+        if own:
+            eng.set_X(X)
+            eng.set_pathways(_as_packed(pathways, nodelist, n))
+        eng.set_UV(U, V)
+        eng.set_active(active)
+        return _obj_dict(eng.objective(gamma, delta))
+    finally:
+        if own:
+            eng.close()
+
+
 def latent_pathway_tables(V, pathways, nodelist=None, engine=None):
     """(mass, quad_norm, quad_raw), each k x P, for a host V (score/restrict/force_distinct/find_mins)."""
     V = np.asarray(V, dtype=np.float64)

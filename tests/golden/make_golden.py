@@ -215,7 +215,10 @@ def save_cli_case():
         fps = write_cli_inputs(tmp, X, nodelist, Gs)
         os.chdir(tmp)
         rel = [os.path.basename(f) for f in fps]
-        for tag, extra in (("nonorm", ["--no-normalize"]), ("norm", [])):
+        init_order = [rel[i] for i in (3, 1, 5, 0, 2, 4)]      # exactly k files: no set-order-dependent sampling
+        for tag, extra in (("nonorm", ["--no-normalize"]), ("norm", []),
+                           ("init", ["--no-normalize", "--manifolds-init"] + init_order),
+                           ("cv", ["--no-normalize", "--cross-validation", "0.2"])):
             ref_shim.reset_globals(R)
             argv = ["prmf_runner.py", "--data", "data.tsv", "--manifolds"] + rel + [
                 "--node-attribute", "name", "--nodelist", "nodelist.txt", "--outdir", ".", "--delimiter", "\t",
@@ -229,8 +232,9 @@ def save_cli_case():
                 sys.argv = old
             dst = os.path.join(HERE, "cli_test1_" + tag)
             os.makedirs(dst, exist_ok=True)
-            for f in ("obj.txt", "U.csv", "V.csv"):
-                shutil.copy(os.path.join(tmp, f), os.path.join(dst, f))
+            for f in ("obj.txt", "U.csv", "V.csv", "init_pathways.txt", "test_error.csv"):
+                if os.path.exists(os.path.join(tmp, f)):
+                    shutil.move(os.path.join(tmp, f), os.path.join(dst, f))
             with open(os.path.join(dst, "stdout_head.txt"), "w") as fh:
                 fh.write("\n".join(out.getvalue().splitlines()[:12]) + "\n")
             print("cli_test1_%-21s %s" % (tag, open(os.path.join(dst, "obj.txt")).read().splitlines()[6]))

@@ -96,8 +96,10 @@ def _compare_outputs(tmp_path, tag):
     exp = os.path.join(GOLDEN, "cli_test1_" + tag)
     got_obj = open(tmp_path / "obj.txt").read().splitlines()
     exp_obj = open(os.path.join(exp, "obj.txt")).read().splitlines()
-    assert got_obj[7:] == exp_obj[7:], "factor -> graphml lines differ"
-    for a, b in zip(got_obj[:7], exp_obj[:7]):
+    nkv = sum(1 for line in exp_obj if " = " in line)
+    assert len(got_obj) == len(exp_obj)
+    assert got_obj[nkv:] == exp_obj[nkv:], "factor -> graphml lines differ"
+    for a, b in zip(got_obj[:nkv], exp_obj[:nkv]):
         ka, va = a.split(" = "); kb, vb = b.split(" = ")
         assert ka == kb
         np.testing.assert_allclose(float(va), float(vb), rtol=1e-6, atol=2e-5)    # values are printed to 5 decimals
@@ -140,3 +142,34 @@ def test_cli_inferred_nodelist_gives_same_result(tmp_path):
     code, out, err = _main(argv, tmp_path)
     assert code == 0, err[-2000:]
     _compare_outputs(tmp_path, "nonorm")
+
+
+@pytest.mark.gpu
+def test_cli_manifolds_init_matches_reference(tmp_path):
+    """--manifolds-init with exactly k files: pathway_to_vec + two NNLS solves per factor (:272-334, :1023-1064)."""
+    rel = _write_inputs(tmp_path)
+    order = [rel[i] for i in (3, 1, 5, 0, 2, 4)]
+    argv = ["--data", "data.tsv", "--manifolds"] + rel + ["--node-attribute", "name", "--nodelist", "nodelist.txt",
+                                                           "--outdir", ".", "--delimiter", "\t", "--seed", "1",
+                                                           "--no-normalize", "--manifolds-init"] + order
+    code, out, err = _main(argv, tmp_path)
+    assert code == 0, err[-2000:]
+    assert "Using the following manifolds for initialization:" in out
+    assert open(tmp_path / "init_pathways.txt").read() == open(
+        os.path.join(GOLDEN, "cli_test1_init", "init_pathways.txt")).read()
+    _compare_outputs(tmp_path, "init")
+
+
+@pytest.mark.gpu
+def test_cli_cross_validation_matches_reference(tmp_path):
+    """--cross-validation 0.2: first KFold split held out, per-sample NNLS test error (:1004-1013, :1074-1079)."""
+    rel = _write_inputs(tmp_path)
+    argv = ["--data", "data.tsv", "--manifolds"] + rel + ["--node-attribute", "name", "--nodelist", "nodelist.txt",
+                                                           "--outdir", ".", "--delimiter", "\t", "--seed", "1",
+                                                           "--no-normalize", "--cross-validation", "0.2"]
+    code, out, err = _main(argv, tmp_path)
+    assert code == 0, err[-2000:]
+    _compare_outputs(tmp_path, "cv")
+    got = np.loadtxt(tmp_path / "test_error.csv", delimiter=",")
+    ref = np.loadtxt(os.path.join(GOLDEN, "cli_test1_cv", "test_error.csv"), delimiter=",")
+    np.testing.assert_allclose(got, ref, rtol=1e-6)

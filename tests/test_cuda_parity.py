@@ -180,3 +180,16 @@ def test_full_size_properties():
         parts, _, _ = eng.step(9, gamma, delta)
         np.testing.assert_allclose(parts[-1, 7], eng.residual_sq(), rtol=1e-10)
         assert np.all(np.diff(parts[:, 4]) < 0), "objective should decrease with fixed pathways"
+
+
+def test_standalone_objective_matches_oracle():
+    """nmf_manifold_vec_obj seam (:336-372) on arbitrary U, V (explicit residual pass)."""
+    from oracle import prmf_oracle as O
+    from prmf_b200 import nmf_manifold_vec_obj
+    X, nodelist, Gs, U, V, active = _instance(90, 260, 5, 7, seed=31, weighted=True)
+    tables = O.PathwayTables(Gs, nodelist)
+    ref = O.objective(X, U, V, tables, active, 3.5, 0.25)
+    got = nmf_manifold_vec_obj(X, U, V, Gs, active, gamma=3.5, delta=0.25, nodelist=nodelist)
+    for key in ("recon", "manifold", "ignore", "fro", "obj"):
+        np.testing.assert_allclose(got[key], ref[key], rtol=1e-12)
+    assert list(got) == ["recon", "manifold", "ignore", "fro", "gamma", "delta", "obj"]

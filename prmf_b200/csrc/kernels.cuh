@@ -99,6 +99,29 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
     return scratch[0];
 }
 
+// Deterministic block reduction of NV values at once (one shared-memory round instead of NV); results valid in
+// thread 0.  `scratch` holds >= 32*NV doubles.
+template <int NV>
+__device__ __forceinline__ void block_sum_multi(double (&v)[NV], double* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) scratch[i * 32 + warp] = v[i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double t = lane < nw ? scratch[i * 32 + lane] : 0.0;
+            v[i] = warp_sum(t);
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------------------------------
 // ||X||_F^2  (np.linalg.norm(X), :640) : per-block partials, summed in order by sum_partials_kernel
 // ----------------------------------------------------------------------------------------------------
@@ -134,6 +157,7 @@ __global__ void sum_partials_kernel(const double* __restrict__ part, int count, 
 // into NS slices so every thread has work (item = slice * k*k + pair).  Slices are combined in a fixed order.
 // ----------------------------------------------------------------------------------------------------
 constexpr int kTailThreads = 1024;
+constexpr int kVhCap = 4096;          // staged (support gene, factor) values in the objective (32 KB of smem)
 
 __host__ __device__ inline int gram_slices(int k) {
     const int kk2 = k * k;
@@ -647,6 +671,8 @@ struct ActiveSet {
     const double* diag_coef;     // isd_r * diag(L)_r * isd_r
     const int32_t* off_r;        // gene of the row
     const int32_t* off_c;        // gene of the neighbour
+    const int32_t* off_lr;       // index of the row's diagonal entry (0..n_diag)
+    const int32_t* off_lc;       // index of the neighbour's diagonal entry
     const int32_t* off_factor;
     const double* off_coef;      // isd_r * (-w_rc * isd_c)   (0 for a self loop: it is part of diag(L))
 };
@@ -658,6 +684,7 @@ __global__ void build_active_kernel(Pathways pw, const int32_t* __restrict__ act
                                     int32_t* __restrict__ pos, int32_t* __restrict__ diag_gene,
                                     int32_t* __restrict__ diag_factor, double* __restrict__ diag_coef,
                                     int32_t* __restrict__ off_r, int32_t* __restrict__ off_c,
+                                    int32_t* __restrict__ off_lr, int32_t* __restrict__ off_lc,
                                     int32_t* __restrict__ off_factor, double* __restrict__ off_coef) {
     const int c = blockIdx.y;
     const int p = active[c];
@@ -676,11 +703,26 @@ __global__ void build_active_kernel(Pathways pw, const int32_t* __restrict__ act
             const int64_t rc = beg + pw.col_local[e2];
             off_r[oi] = g;
             off_c[oi] = pw.support_idx[rc];
+            off_lr[oi] = (int32_t)di;
+            off_lc[oi] = (int32_t)(doff[c] + (rc - beg));
             off_factor[oi] = c;
             off_coef[oi] = (rc == r) ? 0.0 : ir * (-pw.w[e2] * pw.isd[rc]);
         }
     }
 }
+
+#ifdef PRMF_TAIL_TIMING
+// Developer instrumentation (not part of the product build): phase time stamps of the V-update kernel.
+__device__ unsigned long long g_tail_dbg[16];
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TAIL_STAMP(i, cond) do { if (threadIdx.x == 0 && (cond)) g_tail_dbg[i] = gtime(); } while (0)
+#else
+#define TAIL_STAMP(i, cond) do { } while (0)
+#endif
 
 // ----------------------------------------------------------------------------------------------------
 // Objective of one inner step (:336-372) without a pass over X, and the tradeoff feedback (:542-548).
@@ -698,17 +740,59 @@ __device__ __forceinline__ void objective_block(const double* __restrict__ V, in
                                                 const double* __restrict__ normX_sq, const ActiveSet& as,
                                                 double* __restrict__ Gv, double* __restrict__ gd, double tradeoff,
                                                 double* __restrict__ obj_out, int* __restrict__ step_counter,
-                                                int obj_capacity) {
+                                                int obj_capacity, double* __restrict__ sVh, int vh_cap) {
     const int kk2 = k * k;
     const int t = threadIdx.x;
+    // prefetch everything that does not depend on Gv_new: scalars, VB partials, the flattened-Laplacian entries
+    const double gamma = gd[0], delta = gd[1], nx2 = normX_sq[0];
+    double vb = 0.0;
+    for (int b = t; b < vblocks; b += blockDim.x) vb += __ldcg(VB_part + b);
+    // One SM runs this block, and every scattered gather costs it an L1 wavefront: gather each distinct
+    // (support gene, factor) value ONCE into shared memory (n_diag of them) and let the ~5x more numerous
+    // off-diagonal entries index that copy.  Falls back to global gathers when n_diag exceeds the buffer.
+    const bool staged = as.n_diag <= vh_cap;
+    if (staged)
+        for (int64_t i = t; i < as.n_diag; i += blockDim.x)
+            sVh[i] = __ldcg(V + (int64_t)as.diag_gene[i] * k + as.diag_factor[i]);
+    constexpr int kPre = 4;                       // entries per thread handled from registers (4096 per pass)
+    int dfac[kPre], ofac[kPre];
+    double dcoef[kPre], dv[kPre], ocoef[kPre], ovr[kPre], ovc[kPre];
+#pragma unroll
+    for (int q = 0; q < kPre; ++q) {
+        const int64_t i = t + (int64_t)q * blockDim.x;
+        dfac[q] = -1; ofac[q] = -1; dcoef[q] = dv[q] = ocoef[q] = ovr[q] = ovc[q] = 0.0;
+        if (staged) continue;
+        if (i < as.n_diag) {
+            dfac[q] = as.diag_factor[i];
+            dcoef[q] = as.diag_coef[i];
+            dv[q] = __ldcg(V + (int64_t)as.diag_gene[i] * k + dfac[q]);
+        }
+        if (i < as.n_off) {
+            ofac[q] = as.off_factor[i];
+            ocoef[q] = as.off_coef[i];
+            ovr[q] = __ldcg(V + (int64_t)as.off_r[i] * k + ofac[q]);
+            ovc[q] = __ldcg(V + (int64_t)as.off_c[i] * k + ofac[q]);
+        }
+    }
+    TAIL_STAMP(6, true);
+    // Gv_new[e] = fixed-order sum of the V-update blocks' partials (slices in parallel, then slice sums in order)
     if (kk2 <= 1024) {
         const int nsl = 1024 / kk2;
         const int per = (vblocks + nsl - 1) / nsl;
         if (t < nsl * kk2) {
             const int e = t % kk2, sl = t / kk2;
             const int b0 = sl * per, cnt = max(0, min(vblocks, b0 + per) - b0);
+            const double* src = Gv_part + (int64_t)b0 * kk2 + e;
             double s2 = 0.0;
-            for (int b = 0; b < cnt; ++b) s2 += __ldcg(Gv_part + (int64_t)(b0 + b) * kk2 + e);
+            int b = 0;
+            for (; b + 8 <= cnt; b += 8) {
+                double tmp[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) tmp[q] = __ldcg(src + (int64_t)(b + q) * kk2);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) s2 += tmp[q];
+            }
+            for (; b < cnt; ++b) s2 += __ldcg(src + (int64_t)b * kk2);
             sSl[sl * kk2 + e] = s2;
         }
         __syncthreads();
@@ -727,36 +811,60 @@ __device__ __forceinline__ void objective_block(const double* __restrict__ V, in
         }
     }
     __syncthreads();
+    TAIL_STAMP(7, true);
+    double* sNrm = scratch + 5 * 32;              // ||v_c|| per factor (:345), computed once
+    for (int c = t; c < k; c += blockDim.x) sNrm[c] = sqrt(sGv[c * k + c]);
     double gg = 0.0, fr = 0.0;
     for (int e = t; e < kk2; e += blockDim.x) {
         const double gu = sGu[e];
         gg = fma(sGv[e], gu, gg);
         if (e / k == e % k) fr += gu;                                                       // :359
     }
-    double vb = 0.0;
-    for (int b = t; b < vblocks; b += blockDim.x) vb += __ldcg(VB_part + b);
+    __syncthreads();
     double man = 0.0, ign = 0.0;
-    for (int64_t i = t; i < as.n_diag; i += blockDim.x) {
-        const int c = as.diag_factor[i];
-        const double vr = __ldcg(V + (int64_t)as.diag_gene[i] * k + c) / sqrt(sGv[c * k + c]);   // :345
-        man = fma(as.diag_coef[i] * vr, vr, man);
-        ign += 1.0 / (vr + 1.0);                                                            // :352
+    if (staged) {
+        for (int64_t i = t; i < as.n_diag; i += blockDim.x) {
+            const double vr = sVh[i] / sNrm[as.diag_factor[i]];                             // :345
+            sVh[i] = vr;
+            man = fma(as.diag_coef[i] * vr, vr, man);
+            ign += 1.0 / (vr + 1.0);                                                        // :352
+        }
+        __syncthreads();
+        for (int64_t i = t; i < as.n_off; i += blockDim.x)
+            man = fma(as.off_coef[i] * sVh[as.off_lc[i]], sVh[as.off_lr[i]], man);          // :350
     }
-    for (int64_t i = t; i < as.n_off; i += blockDim.x) {
+#pragma unroll
+    for (int q = 0; q < kPre; ++q) {
+        if (dfac[q] >= 0) {
+            const double vr = dv[q] / sNrm[dfac[q]];                                        // :345
+            man = fma(dcoef[q] * vr, vr, man);
+            ign += 1.0 / (vr + 1.0);                                                        // :352
+        }
+        if (ofac[q] >= 0) {
+            const double nrm = sNrm[ofac[q]];
+            man = fma(ocoef[q] * (ovc[q] / nrm), ovr[q] / nrm, man);                        // :350
+        }
+    }
+    for (int64_t i = t + (int64_t)kPre * blockDim.x; !staged && i < as.n_diag; i += blockDim.x) {
+        const int c = as.diag_factor[i];
+        const double vr = __ldcg(V + (int64_t)as.diag_gene[i] * k + c) / sNrm[c];
+        man = fma(as.diag_coef[i] * vr, vr, man);
+        ign += 1.0 / (vr + 1.0);
+    }
+    for (int64_t i = t + (int64_t)kPre * blockDim.x; !staged && i < as.n_off; i += blockDim.x) {
         const int c = as.off_factor[i];
-        const double nrm = sqrt(sGv[c * k + c]);
+        const double nrm = sNrm[c];
         const double vr = __ldcg(V + (int64_t)as.off_r[i] * k + c) / nrm;
         const double vc = __ldcg(V + (int64_t)as.off_c[i] * k + c) / nrm;
-        man = fma(as.off_coef[i] * vc, vr, man);                                            // :350
+        man = fma(as.off_coef[i] * vc, vr, man);
     }
-    const double GG = block_sum(gg, scratch);
-    const double FRO = block_sum(fr, scratch);
-    const double VB = block_sum(vb, scratch);
-    const double MAN = block_sum(man, scratch);
-    const double IGN = block_sum(ign, scratch);
+    TAIL_STAMP(8, true);
+    double red5[5] = {gg, fr, vb, man, ign};
+    block_sum_multi<5>(red5, scratch);
+    TAIL_STAMP(9, true);
     if (t == 0) {
-        const double gamma = gd[0], delta = gd[1];
-        const double r2 = normX_sq[0] - 2.0 * VB + GG;
+        const double GG = red5[0], FRO = red5[1], VB = red5[2], MAN = red5[3], IGN = red5[4];
+        const double r2 = nx2 - 2.0 * VB + GG;
         const double recon = sqrt(r2 > 0.0 ? r2 : 0.0);
         const double obj = recon + gamma * MAN + delta * IGN + FRO;                         // :362
         const int s2 = *step_counter;
@@ -782,6 +890,8 @@ __device__ __forceinline__ void objective_block(const double* __restrict__ V, in
 // step in between, which every peer reaches only after it finished reading parity p.
 // ----------------------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 8;
+
+
 
 struct PeerExchange {
     int nranks;                                // 0: no exchange (one GPU, or the NCCL path)
@@ -831,7 +941,7 @@ __device__ __forceinline__ double sum_peers(const PeerExchange& px, int64_t idx)
 //   den < eps -> eps ; V <- V*num/den ; V < eps -> eps
 // V is double-buffered: pathway neighbours of a gene may be updated by another block, so new values go to Vnew
 // while every block reads the untouched Vold.  Every block leaves partials of V_new^T V_new and
-// sum(V_new * B); the last block to finish (atomic ticket) evaluates the objective from them.
+// sum(V_new * B); block 0 waits for the others (atomic ticket) and evaluates the objective from them.
 // ----------------------------------------------------------------------------------------------------
 template <int NI>
 __global__ void __launch_bounds__(kTailThreads)
@@ -850,11 +960,12 @@ v_update_objective_kernel(const double* __restrict__ Vold, double* __restrict__ 
     // Two k*k arrays do not fit for k > 64 (2 x 128 KB at k = 128): then the objective keeps Gv_new in global
     // memory and the second slot shrinks to the 1024-double slice buffer (the host sizes smem the same way).
     double* sV = sm + k * k + (k > 64 ? 1024 : k * k);   // max(rows_per_tile*k, 1024): new V rows / slice sums
-    __shared__ double scratch[32];
-    __shared__ int s_last;
+    double* sVh = sV + max(rows_per_tile * k, 1024);     // kVhCap doubles: unit-vector values of the active supports
+    __shared__ double scratch[5 * 32 + 128];    // block reductions + per-factor norms (k <= 128)
     const int kk2 = k * k;
     const int ns = gram_slices(k);
     const int64_t nk_all = (int64_t)n * k;
+    TAIL_STAMP(0, blockIdx.x == 0);
     if (px.nranks > 0) {
         peer_barrier(px);
         for (int i = threadIdx.x; i < kk2; i += blockDim.x) sGu[i] = sum_peers(px, nk_all + i);
@@ -868,6 +979,7 @@ v_update_objective_kernel(const double* __restrict__ Vold, double* __restrict__ 
     for (int q = 0; q < NI; ++q) gacc[q] = 0.0;
     double vb = 0.0;
     __syncthreads();
+    TAIL_STAMP(1, blockIdx.x == 0);
     const int ntiles = (n + rows_per_tile - 1) / rows_per_tile;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int j0 = tile * rows_per_tile;
@@ -902,25 +1014,36 @@ v_update_objective_kernel(const double* __restrict__ Vold, double* __restrict__ 
             vb = fma(vn, b, vb);
         }
         __syncthreads();
+        TAIL_STAMP(2, blockIdx.x == 0);
         gram_accumulate<NI>(sV, rows, rows_per_tile, k, ns, gacc);
         __syncthreads();
     }
     gram_store<NI>(sV, k, ns, gacc, Gv_part + (int64_t)blockIdx.x * kk2);
     const double tvb = block_sum(vb, scratch);
     if (threadIdx.x == 0) VB_part[blockIdx.x] = tvb;
-    // ---- last block done: objective ----
+    TAIL_STAMP(3, blockIdx.x == 0);
+    // ---- objective: block 0 waits for the other blocks (they never wait on anything, so this cannot deadlock)
+    //      and evaluates it.  Always the same block, hence the same SM from launch to launch: the objective's
+    //      code stays in that SM's instruction cache (with a "last block done" scheme a random, cold SM ran it).
     __threadfence();
     __syncthreads();
+    if (blockIdx.x != 0) {
+        if (threadIdx.x == 0) atomicAdd(ticket, 1u);
+        return;
+    }
     if (threadIdx.x == 0) {
-        const unsigned int tk = atomicAdd(ticket, 1u);
-        s_last = (tk == gridDim.x - 1) ? 1 : 0;
+        unsigned int seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ticket) : "memory");
+        } while (seen < gridDim.x - 1);
     }
     __syncthreads();
-    if (!s_last) return;
+    TAIL_STAMP(4, true);
     if (threadIdx.x == 0) *ticket = 0u;                 // re-arm for the next launch
-    __threadfence();
+    // (the other blocks' results are read with ld.global.cg from L2, where their fenced writes already are)
     objective_block(Vnew, k, sGu, k > 64 ? Gv : sGv, k > 64 ? sGv : sV, scratch, Gv_part, VB_part, (int)gridDim.x, normX_sq,
-                    as, Gv, gd, tradeoff, obj_out, step_counter, obj_capacity);
+                    as, Gv, gd, tradeoff, obj_out, step_counter, obj_capacity, sVh, kVhCap);
+    TAIL_STAMP(5, true);
 }
 
 // Gram of V from scratch (after prmf_set_UV): same tiling as the update kernel so partial layout matches.

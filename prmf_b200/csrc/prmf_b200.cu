@@ -35,6 +35,23 @@ struct DevBuf {
 
 }  // namespace
 
+// Bump allocator over ONE cudaMalloc.  All small state of a handle lives in a few contiguous 2 MB pages: after
+// 2 GB of X have streamed through, every first touch of a separately allocated small buffer is a TLB miss, and the
+// latency-bound tail kernels pay for each of them in sequence.
+struct Arena {
+    unsigned char* base = nullptr;
+    size_t cap = 0, used = 0;
+    template <typename T>
+    T* take(size_t count) {
+        const size_t bytes = ((count ? count : 1) * sizeof(T) + 255) & ~(size_t)255;
+        if (used + bytes > cap) return nullptr;
+        T* p = reinterpret_cast<T*>(base + used);
+        used += bytes;
+        return p;
+    }
+    void release() { if (base) cudaFree(base); base = nullptr; cap = used = 0; }
+};
+
 struct prmf_handle {
     int device = 0;
     int sm_count = 148;
@@ -46,7 +63,8 @@ struct prmf_handle {
     bool own_stream = false;
     std::string err;
 
-    // device buffers
+    // device buffers (everything but X, Xt and the peer-exchange buffer comes out of the arenas)
+    Arena arena, pw_arena, as_arena;
     double *X = nullptr, *Xt = nullptr;       // samples x genes, and its transposed copy genes x samples
     double *U = nullptr, *Vbuf[2] = {nullptr, nullptr}, *Ub = nullptr, *Vb = nullptr, *Gvb = nullptr;
     int vcur = 0;                             // Vbuf[vcur] is the current V
@@ -74,7 +92,6 @@ struct prmf_handle {
     // pathways
     Pathways pw{};
     int64_t S = 0, E = 0;
-    std::vector<void*> pw_allocs;
     std::vector<int64_t> path_ptr_host;
     std::vector<int32_t> support_host;
 
@@ -331,7 +348,7 @@ size_t uu_smem(const prmf_handle* h) {
 size_t vu_smem(const prmf_handle* h) {
     const size_t kk2 = (size_t)h->k * h->k;
     // sGu + (sGv when k <= 64; for larger k that slot only holds the 1024-double slice buffer) + V tile
-    return sizeof(double) * (kk2 + (h->k > 64 ? 1024 : kk2) + std::max<size_t>((size_t)h->vu_rows * h->k, 1024));
+    return sizeof(double) * (kk2 + (h->k > 64 ? 1024 : kk2) + std::max<size_t>((size_t)h->vu_rows * h->k, 1024) + kVhCap);
 }
 size_t gram_smem(const prmf_handle* h) { return sizeof(double) * ((size_t)h->vu_rows * h->k); }
 
@@ -400,21 +417,27 @@ int ensure_pos(prmf_handle* h) {
     const int64_t nd = offs[k], no = offs[2 * k + 1];
     if (nd > h->as_cap_diag || no > h->as_cap_off || !h->as_i32) {
         CU(cudaStreamSynchronize(h->stream));
-        if (h->as_i32) cudaFree(h->as_i32);
-        if (h->as_f64) cudaFree(h->as_f64);
-        h->as_i32 = nullptr; h->as_f64 = nullptr;
+        h->as_arena.release();
         h->as_cap_diag = std::max<int64_t>(nd * 2, 1024);
         h->as_cap_off = std::max<int64_t>(no * 2, 4096);
-        int rc = dalloc(h, &h->as_i32, (size_t)(2 * h->as_cap_diag + 3 * h->as_cap_off));
-        if (rc) return rc;
-        if ((rc = dalloc(h, &h->as_f64, (size_t)(h->as_cap_diag + h->as_cap_off)))) return rc;
+        const size_t n_i32 = (size_t)(2 * h->as_cap_diag + 5 * h->as_cap_off);
+        const size_t n_f64 = (size_t)(h->as_cap_diag + h->as_cap_off);
+        const size_t total = ((n_i32 * 4 + 255) & ~(size_t)255) + ((n_f64 * 8 + 255) & ~(size_t)255) +
+                             ((sizeof(int64_t) * 2 * (k + 1) + 255) & ~(size_t)255);
+        cudaError_t ea = cudaMalloc((void**)&h->as_arena.base, total);
+        if (ea != cudaSuccess) return fail(h, PRMF_ERR_NOMEM, "cudaMalloc active set: %s", cudaGetErrorString(ea));
+        h->as_arena.cap = total;
+        h->as_f64 = h->as_arena.take<double>(n_f64);
+        h->as_i32 = h->as_arena.take<int32_t>(n_i32);
+        h->as_off = h->as_arena.take<int64_t>((size_t)2 * (k + 1));
     }
-    if (!h->as_off) { int rc = dalloc(h, &h->as_off, (size_t)2 * (k + 1)); if (rc) return rc; }
     int32_t* dg = h->as_i32;
     int32_t* df = dg + h->as_cap_diag;
     int32_t* orr = df + h->as_cap_diag;
     int32_t* occ = orr + h->as_cap_off;
-    int32_t* of = occ + h->as_cap_off;
+    int32_t* olr = occ + h->as_cap_off;
+    int32_t* olc = olr + h->as_cap_off;
+    int32_t* of = olc + h->as_cap_off;
     double* dc = h->as_f64;
     double* oc = dc + h->as_cap_diag;
     CU(cudaMemcpyAsync(h->as_off, offs.data(), sizeof(int64_t) * offs.size(), cudaMemcpyHostToDevice, h->stream));
@@ -422,11 +445,11 @@ int ensure_pos(prmf_handle* h) {
     CU(cudaMemsetAsync(h->pos, 0xff, sizeof(int32_t) * h->n * h->k, h->stream));
     dim3 grid(4, h->k);
     build_active_kernel<<<grid, 128, 0, h->stream>>>(h->pw, h->active, k, h->as_off, h->as_off + (k + 1), h->pos, dg, df,
-                                                     dc, orr, occ, of, oc);
+                                                     dc, orr, occ, olr, olc, of, oc);
     LAUNCH_CHECK("build_active_kernel");
     h->as.n_diag = nd; h->as.n_off = no;
     h->as.diag_gene = dg; h->as.diag_factor = df; h->as.diag_coef = dc;
-    h->as.off_r = orr; h->as.off_c = occ; h->as.off_factor = of; h->as.off_coef = oc;
+    h->as.off_r = orr; h->as.off_c = occ; h->as.off_lr = olr; h->as.off_lc = olc; h->as.off_factor = of; h->as.off_coef = oc;
     h->pos_dirty = false;
     return PRMF_OK;
 }
@@ -441,12 +464,7 @@ int allreduce(prmf_handle* h, double* buf, size_t count) {
 
 int ensure_obj_capacity(prmf_handle* h, int n_steps) {
     if (n_steps <= h->obj_capacity) return PRMF_OK;
-    if (h->obj) cudaFree(h->obj);
-    int cap = std::max(n_steps, 64);
-    int rc = dalloc(h, &h->obj, (size_t)cap * kObjStride);
-    if (rc) return rc;
-    h->obj_capacity = cap;
-    return PRMF_OK;
+    return fail(h, PRMF_ERR_ARG, "at most %d inner steps per prmf_step call", h->obj_capacity);
 }
 
 cudaEvent_t get_event(prmf_handle* h, int* idx) {
@@ -656,26 +674,46 @@ int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global
     const int64_t nk = n * k;
     const int kk2 = k * k;
     const int64_t pad_rows = 16;      // bulk copies of W read up to one stage past the last row
+    h->obj_capacity = 256;
+    {
+        auto pad = [](size_t count, size_t elem) { return ((count ? count : 1) * elem + 255) & ~(size_t)255; };
+        const size_t d = sizeof(double);
+        size_t total = 0;
+        total += 2 * pad((size_t)(m_local + pad_rows) * k, d);                                      // U, Ub
+        total += pad((size_t)std::max(h->chunks1, h->tchunks1) * std::max<int64_t>(1, m_local) * k, d);   // Apart
+        total += 2 * pad((size_t)(n + pad_rows) * k, d) + pad((size_t)nk, d);                      // Vbuf[2], Vb
+        total += 2 * pad(kk2, d) + pad((size_t)h->uu_grid * kk2, d) + pad((size_t)h->vu_grid * kk2, d);
+        total += pad(h->vu_grid, d) + pad((size_t)std::max(h->chunks, h->tchunks) * nk, d);       // VB_part, Bpart
+        total += pad((size_t)nk + kk2 + 2, d) + pad(1, d) + pad((size_t)h->sm_count * 8, d) + pad(2, d);
+        total += pad(1, sizeof(int)) + pad(1, sizeof(unsigned int)) + pad(k, sizeof(int32_t)) + pad(nk, sizeof(int32_t));
+        total += pad((size_t)h->obj_capacity * kObjStride, d);
+        cudaError_t ea = cudaMalloc((void**)&h->arena.base, total);
+        if (ea != cudaSuccess) rc = fail(h, PRMF_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", total, cudaGetErrorString(ea));
+        h->arena.cap = total;
+    }
 #define ALLOC(ptr, count) if (!rc) rc = dalloc(h, &ptr, (size_t)(count))
+#define TAKE(ptr, T, count) if (!rc) { ptr = h->arena.take<T>((size_t)(count)); if (!ptr) rc = fail(h, PRMF_ERR_NOMEM, "arena exhausted"); }
     ALLOC(h->X, (size_t)std::max<int64_t>(1, m_local) * h->ldx);
     ALLOC(h->Xt, (size_t)n * h->ldxt);
-    ALLOC(h->U, (m_local + pad_rows) * k);
-    ALLOC(h->Ub, (m_local + pad_rows) * k);
-    ALLOC(h->Apart, (size_t)std::max(h->chunks1, h->tchunks1) * std::max<int64_t>(1, m_local) * k);
-    ALLOC(h->Vbuf[0], (n + pad_rows) * k); ALLOC(h->Vbuf[1], (n + pad_rows) * k); ALLOC(h->Vb, nk);
-    ALLOC(h->Gv, kk2); ALLOC(h->Gvb, kk2);
-    ALLOC(h->Gu_part, (size_t)h->uu_grid * kk2);
-    ALLOC(h->Gv_part, (size_t)h->vu_grid * kk2);
-    ALLOC(h->VB_part, h->vu_grid);
-    ALLOC(h->Bpart, (size_t)std::max(h->chunks, h->tchunks) * nk);
-    ALLOC(h->red, (size_t)nk + kk2 + 2);
-    ALLOC(h->normX_sq, 1);
-    ALLOC(h->scal_part, (size_t)h->sm_count * 8);
-    ALLOC(h->gd, 2);
-    ALLOC(h->step_counter, 1);
-    ALLOC(h->ticket, 1);
-    ALLOC(h->active, k);
-    ALLOC(h->pos, nk);
+    TAKE(h->U, double, (m_local + pad_rows) * k);
+    TAKE(h->Ub, double, (m_local + pad_rows) * k);
+    TAKE(h->Apart, double, (size_t)std::max(h->chunks1, h->tchunks1) * std::max<int64_t>(1, m_local) * k);
+    TAKE(h->Vbuf[0], double, (n + pad_rows) * k); TAKE(h->Vbuf[1], double, (n + pad_rows) * k); TAKE(h->Vb, double, nk);
+    TAKE(h->Gv, double, kk2); TAKE(h->Gvb, double, kk2);
+    TAKE(h->Gu_part, double, (size_t)h->uu_grid * kk2);
+    TAKE(h->Gv_part, double, (size_t)h->vu_grid * kk2);
+    TAKE(h->VB_part, double, h->vu_grid);
+    TAKE(h->Bpart, double, (size_t)std::max(h->chunks, h->tchunks) * nk);
+    TAKE(h->red, double, (size_t)nk + kk2 + 2);
+    TAKE(h->normX_sq, double, 1);
+    TAKE(h->scal_part, double, (size_t)h->sm_count * 8);
+    TAKE(h->gd, double, 2);
+    TAKE(h->step_counter, int, 1);
+    TAKE(h->ticket, unsigned int, 1);
+    TAKE(h->active, int32_t, k);
+    TAKE(h->pos, int32_t, nk);
+    TAKE(h->obj, double, (size_t)h->obj_capacity * kObjStride);
+#undef TAKE
 #undef ALLOC
     if (!rc) {
         cudaMemsetAsync(h->Xt, 0, sizeof(double) * n * h->ldxt, h->stream);
@@ -717,11 +755,11 @@ int prmf_destroy(prmf_handle* h) {
             if (r != h->rank && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
     if (h->p2p_buf) cudaFree(h->p2p_buf);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-    void* bufs[] = {h->X, h->Xt, h->U, h->Vbuf[0], h->Vbuf[1], h->Ub, h->Vb, h->Gvb, h->Apart, h->Gv, h->Gu_part,
-                    h->Gv_part, h->VB_part, h->Bpart, h->red, h->normX_sq, h->scal_part, h->gd, h->obj,
-                    h->step_counter, h->active, h->pos, h->scores_buf, h->as_i32, h->as_f64, h->as_off, h->ticket};
-    for (void* b : bufs) if (b) cudaFree(b);
-    for (void* b : h->pw_allocs) cudaFree(b);
+    if (h->X) cudaFree(h->X);
+    if (h->Xt) cudaFree(h->Xt);
+    h->arena.release();
+    h->pw_arena.release();
+    h->as_arena.release();
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return PRMF_OK;
@@ -792,16 +830,23 @@ int prmf_set_pathways(prmf_handle* h, int32_t P, const int64_t* path_ptr, const 
     }
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
-    for (void* b : h->pw_allocs) cudaFree(b);
-    h->pw_allocs.clear();
+    h->pw_arena.release();
+    {
+        auto pad = [](size_t bytes) { return (bytes + 255) & ~(size_t)255; };
+        const size_t total = pad(sizeof(int64_t) * (P + 1)) + pad(sizeof(int32_t) * std::max<int64_t>(1, S)) +
+                             pad(sizeof(int64_t) * (S + 1)) + pad(sizeof(int32_t) * std::max<int64_t>(1, E)) +
+                             pad(sizeof(double) * std::max<int64_t>(1, E)) + 3 * pad(sizeof(double) * std::max<int64_t>(1, S)) +
+                             pad(sizeof(double) * 3 * (size_t)h->k * P);
+        cudaError_t ea = cudaMalloc((void**)&h->pw_arena.base, total);
+        if (ea != cudaSuccess) return fail(h, PRMF_ERR_NOMEM, "cudaMalloc pathways (%zu bytes): %s", total, cudaGetErrorString(ea));
+        h->pw_arena.cap = total;
+    }
     int rc = 0;
     auto up = [&](const void* src, size_t bytes, const void** dst) -> int {
-        void* d = nullptr;
-        cudaError_t e = cudaMalloc(&d, bytes ? bytes : 8);
-        if (e != cudaSuccess) return fail(h, PRMF_ERR_NOMEM, "cudaMalloc pathways: %s", cudaGetErrorString(e));
-        h->pw_allocs.push_back(d);
+        unsigned char* d = h->pw_arena.take<unsigned char>(bytes);
+        if (!d) return fail(h, PRMF_ERR_NOMEM, "pathway arena exhausted");
         if (bytes) {
-            e = cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, h->stream);
+            cudaError_t e = cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, h->stream);
             if (e != cudaSuccess) return fail(h, PRMF_ERR_CUDA, "copy pathways: %s", cudaGetErrorString(e));
         }
         *dst = d;
@@ -819,9 +864,8 @@ int prmf_set_pathways(prmf_handle* h, int32_t P, const int64_t* path_ptr, const 
     if (!rc) rc = up(isd.data(), sizeof(double) * S, (const void**)&pw.isd);
     if (rc) return rc;
     CU(cudaStreamSynchronize(h->stream));
-    if (h->scores_buf) cudaFree(h->scores_buf);
-    h->scores_buf = nullptr;
-    if ((rc = dalloc(h, &h->scores_buf, (size_t)3 * h->k * P))) return rc;
+    h->scores_buf = h->pw_arena.take<double>((size_t)3 * h->k * P);
+    if (!h->scores_buf) return fail(h, PRMF_ERR_NOMEM, "pathway arena exhausted (scores)");
     h->pw = pw; h->S = S; h->E = E;
     h->path_ptr_host.assign(path_ptr, path_ptr + P + 1);
     h->row_ptr_host.assign(row_ptr, row_ptr + S + 1);
@@ -1081,5 +1125,11 @@ int prmf_kernel_times(prmf_handle* h, int reset, double* phase_ms, int64_t* phas
 }
 
 void* prmf_stream(const prmf_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+#ifdef PRMF_TAIL_TIMING
+int prmf_debug_tail_stamps(unsigned long long* out16) {
+    return cudaMemcpyFromSymbol(out16, g_tail_dbg, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 }  // extern "C"

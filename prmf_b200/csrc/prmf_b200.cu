@@ -10,6 +10,7 @@
 //   objective_kernel    Gv_new, recon/manifold/ignore/fro/obj, tradeoff                  (:336-372,:542-548)
 #include "../../include/prmf_b200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -19,6 +20,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "fused.cuh"
 #include "nccl_dyn.h"
 
 using namespace prmf;
@@ -110,6 +112,14 @@ struct prmf_handle {
     int tpanels1 = 0, tpanel_w1 = 0, tchunks1 = 0, tpanels = 0, tpanel_w = 0, tchunks = 0;
     int64_t trows_per_chunk1 = 0, trows_per_chunk = 0;
     size_t tma_smem1 = 0, tma_smem2 = 0;
+
+    // single-pass fused X kernel (opt-in: PRMF_FUSED=1)
+    bool use_fused = false;
+    FusedParams fp{};
+    size_t fused_smem = 0;
+    double *U2 = nullptr, *fEx = nullptr;
+    unsigned long long* fFlags = nullptr;
+    unsigned long long fused_epoch = 0;
 
     // multi-GPU
     NcclComm comm = nullptr;
@@ -266,6 +276,36 @@ int launch_skinny_gen(prmf_handle* h, const double* M, int64_t ldm, int64_t rows
         default: rc = FN<10>(__VA_ARGS__); break; \
     }
 
+template <int K>
+int launch_fused_t(prmf_handle* h) {
+    CU(cudaFuncSetAttribute(fused_xvu_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
+    FusedParams prm = h->fp;
+    void* args[] = {&prm};
+    dim3 grid(h->fp.panels, h->fp.groups);
+    CU(cudaLaunchCooperativeKernel((void*)fused_xvu_kernel<K>, grid, dim3(kFThreads), args, h->fused_smem, h->stream));
+    return PRMF_OK;
+}
+
+// fused step: U update and B partials from ONE pass over X
+int launch_fused(prmf_handle* h) {
+    if (h->m == 0) {
+        CU(cudaMemsetAsync(h->Bpart, 0, sizeof(double) * h->fp.groups * h->n * h->k, h->stream));
+        CU(cudaMemsetAsync(h->Gu_part, 0, sizeof(double) * h->fp.groups * kFExchWarps * h->k * h->k, h->stream));
+        return PRMF_OK;
+    }
+    h->fused_epoch += (1ull << 24);
+    h->fp.Uold = h->U;
+    h->fp.Unew = h->U2;
+    h->fp.V = h->Vbuf[h->vcur];
+    h->fp.epoch = h->fused_epoch;
+    int rc = 0;
+    KT_SWITCH_RC(h->k, rc, launch_fused_t, h);
+    if (rc) return rc;
+    LAUNCH_CHECK("fused_xvu_kernel");
+    std::swap(h->U, h->U2);
+    return PRMF_OK;
+}
+
 // pass 1: A partials = Xt^T . V   (M = Xt: n rows x m cols)
 int launch_xv(prmf_handle* h) {
     if (h->m == 0) return PRMF_OK;
@@ -380,9 +420,9 @@ int launch_v_update_objective(prmf_handle* h, bool sharded, double tradeoff) {
         h->p2p_parity ^= 1;
     }
     const double* Bsrc = sharded ? h->red : h->Bpart;
-    const int bchunks = sharded ? 1 : (h->use_tma ? h->tchunks : h->chunks);
+    const int bchunks = sharded ? 1 : h->use_fused ? h->fp.groups : (h->use_tma ? h->tchunks : h->chunks);
     const double* Gusrc = sharded ? h->red + nk : h->Gu_part;
-    const int gchunks = sharded ? 1 : h->uu_grid;
+    const int gchunks = sharded ? 1 : h->use_fused ? h->fp.groups * kFExchWarps : h->uu_grid;
     NI_SWITCH(h->ni, (v_update_objective_kernel<NI><<<h->vu_grid, kTailThreads, vu_smem(h), h->stream>>>(
                          h->Vbuf[h->vcur], h->Vbuf[h->vcur ^ 1], Bsrc, bchunks, nk, Gusrc, gchunks, (int)h->n, h->k, h->pw,
                          h->active, h->pos, h->gd, h->vu_rows, h->Gv_part, h->VB_part, h->normX_sq, h->as, h->Gv,
@@ -516,18 +556,24 @@ int enqueue_steps(prmf_handle* h, int n_steps, double gamma, double delta, doubl
         cudaEventRecord(h->ev_pool[h->ev_pairs.back().second + 1], h->stream);
     };
     for (int s = 0; s < n_steps; ++s) {
-        tic(0); rc = launch_xv(h); toc();
-        if (rc) return rc;
-        tic(1); rc = launch_u_update(h); toc();
-        if (rc) return rc;
-        tic(2); rc = launch_xtu(h); toc();
-        if (rc) return rc;
+        if (h->use_fused) {
+            tic(0); rc = launch_fused(h); toc();
+            if (rc) return rc;
+        } else {
+            tic(0); rc = launch_xv(h); toc();
+            if (rc) return rc;
+            tic(1); rc = launch_u_update(h); toc();
+            if (rc) return rc;
+            tic(2); rc = launch_xtu(h); toc();
+            if (rc) return rc;
+        }
         const bool sharded = h->comm != nullptr;
         if (sharded) {
             tic(3);
             double* dst = h->p2p_ready ? h->p2p_buf + (size_t)h->p2p_parity * h->p2p_red_count : h->red;
             reduce_pack_kernel<<<(unsigned)((nk + kk2 + 2 + 255) / 256), 256, 0, h->stream>>>(
-                h->Bpart, h->use_tma ? h->tchunks : h->chunks, nk, h->Gu_part, h->uu_grid, h->k, dst);
+                h->Bpart, h->use_fused ? h->fp.groups : (h->use_tma ? h->tchunks : h->chunks), nk, h->Gu_part,
+                h->use_fused ? h->fp.groups * kFExchWarps : h->uu_grid, h->k, dst);
             LAUNCH_CHECK("reduce_pack_kernel");
             if (!h->p2p_ready) rc = allreduce(h, h->red, red_count);      // else: summed inside the V update
             toc();
@@ -670,6 +716,31 @@ int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global
         if (h->tma_smem1 > 220 * 1024 || h->tma_smem2 > 220 * 1024) h->use_tma = false;
     }
 
+    // single-pass fused kernel plan (opt-in)
+    {
+        const char* ef = getenv("PRMF_FUSED");
+        h->use_fused = ef && atoi(ef) == 1 && k <= 10 && n <= 512 * kFMaxPanels;
+        if (h->use_fused) {
+            FusedParams& f = h->fp;
+            f.panels = (int)((n + 511) / 512);
+            f.panel_w = (int)round_up((n + f.panels - 1) / f.panels, 4);
+            f.groups = std::max(1, h->sm_count / f.panels);
+            f.groups = (int)std::min<int64_t>(f.groups, std::max<int64_t>(1, m_local / 64));
+            f.rows_per_group = round_up(std::max<int64_t>(1, (m_local + f.groups - 1) / f.groups), kFRS);
+            uint32_t pitch = (uint32_t)f.panel_w * 8u;
+            while (pitch % 128u != 32u) pitch += 16u;
+            f.pitch = pitch;
+            const size_t stage = (size_t)kFRS * pitch + (((size_t)kFRS * k * 8 + 127) & ~(size_t)127);
+            const size_t fixed = sizeof(double) * ((size_t)kFPaSlots * kFConsWarps * kFRS * kFKP + ((k * k + 1) & ~1)) + 512;
+            int S = (int)((220 * 1024 - fixed) / (stage + sizeof(double) * kFRS * kFKP + 3 * sizeof(uint64_t)));
+            S = std::min(S, 8);
+            f.stages = S;
+            h->fused_smem = (size_t)S * stage + fixed + (size_t)S * (sizeof(double) * kFRS * kFKP + 3 * sizeof(uint64_t));
+            if (S < kFLag + 2 || f.panels * f.groups > h->sm_count) h->use_fused = false;
+            f.ldx = h->ldx; f.m = m_local; f.n = (int)n; f.k = k;
+        }
+    }
+
     int rc = 0;
     const int64_t nk = n * k;
     const int kk2 = k * k;
@@ -679,11 +750,14 @@ int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global
         auto pad = [](size_t count, size_t elem) { return ((count ? count : 1) * elem + 255) & ~(size_t)255; };
         const size_t d = sizeof(double);
         size_t total = 0;
-        total += 2 * pad((size_t)(m_local + pad_rows) * k, d);                                      // U, Ub
+        total += 3 * pad((size_t)(m_local + pad_rows) * k, d);                                      // U, U2, Ub
+        if (h->use_fused)
+            total += pad((size_t)h->fp.groups * kFExSlots * h->fp.panels * kFRS * kFKP, d) +
+                     pad((size_t)h->fp.groups * kFExSlots * h->fp.panels, sizeof(unsigned long long));
         total += pad((size_t)std::max(h->chunks1, h->tchunks1) * std::max<int64_t>(1, m_local) * k, d);   // Apart
         total += 2 * pad((size_t)(n + pad_rows) * k, d) + pad((size_t)nk, d);                      // Vbuf[2], Vb
-        total += 2 * pad(kk2, d) + pad((size_t)h->uu_grid * kk2, d) + pad((size_t)h->vu_grid * kk2, d);
-        total += pad(h->vu_grid, d) + pad((size_t)std::max(h->chunks, h->tchunks) * nk, d);       // VB_part, Bpart
+        total += 2 * pad(kk2, d) + pad((size_t)std::max(h->uu_grid, h->fp.groups * kFExchWarps) * kk2, d) + pad((size_t)h->vu_grid * kk2, d);
+        total += pad(h->vu_grid, d) + pad((size_t)std::max({h->chunks, h->tchunks, h->fp.groups}) * nk, d);   // VB_part, Bpart
         total += pad((size_t)nk + kk2 + 2, d) + pad(1, d) + pad((size_t)h->sm_count * 8, d) + pad(2, d);
         total += pad(1, sizeof(int)) + pad(1, sizeof(unsigned int)) + pad(k, sizeof(int32_t)) + pad(nk, sizeof(int32_t));
         total += pad((size_t)h->obj_capacity * kObjStride, d);
@@ -697,13 +771,18 @@ int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global
     ALLOC(h->Xt, (size_t)n * h->ldxt);
     TAKE(h->U, double, (m_local + pad_rows) * k);
     TAKE(h->Ub, double, (m_local + pad_rows) * k);
+    TAKE(h->U2, double, (m_local + pad_rows) * k);
+    if (h->use_fused) {
+        TAKE(h->fEx, double, (size_t)h->fp.groups * kFExSlots * h->fp.panels * kFRS * kFKP);
+        TAKE(h->fFlags, unsigned long long, (size_t)h->fp.groups * kFExSlots * h->fp.panels);
+    }
     TAKE(h->Apart, double, (size_t)std::max(h->chunks1, h->tchunks1) * std::max<int64_t>(1, m_local) * k);
     TAKE(h->Vbuf[0], double, (n + pad_rows) * k); TAKE(h->Vbuf[1], double, (n + pad_rows) * k); TAKE(h->Vb, double, nk);
     TAKE(h->Gv, double, kk2); TAKE(h->Gvb, double, kk2);
-    TAKE(h->Gu_part, double, (size_t)h->uu_grid * kk2);
+    TAKE(h->Gu_part, double, (size_t)std::max(h->uu_grid, h->fp.groups * kFExchWarps) * kk2);
     TAKE(h->Gv_part, double, (size_t)h->vu_grid * kk2);
     TAKE(h->VB_part, double, h->vu_grid);
-    TAKE(h->Bpart, double, (size_t)std::max(h->chunks, h->tchunks) * nk);
+    TAKE(h->Bpart, double, (size_t)std::max({h->chunks, h->tchunks, h->fp.groups}) * nk);
     TAKE(h->red, double, (size_t)nk + kk2 + 2);
     TAKE(h->normX_sq, double, 1);
     TAKE(h->scal_part, double, (size_t)h->sm_count * 8);
@@ -719,10 +798,16 @@ int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global
         cudaMemsetAsync(h->Xt, 0, sizeof(double) * n * h->ldxt, h->stream);
         cudaMemsetAsync(h->ticket, 0, sizeof(unsigned int), h->stream);
         cudaMemsetAsync(h->U, 0, sizeof(double) * (m_local + pad_rows) * k, h->stream);
+        cudaMemsetAsync(h->U2, 0, sizeof(double) * (m_local + pad_rows) * k, h->stream);
+        if (h->use_fused) {
+            cudaMemsetAsync(h->fFlags, 0, sizeof(unsigned long long) * h->fp.groups * kFExSlots * h->fp.panels, h->stream);
+            h->fp.X = h->X; h->fp.Gv = h->Gv; h->fp.Bpart = h->Bpart; h->fp.Gu_part = h->Gu_part;
+            h->fp.Ex = h->fEx; h->fp.Flags = h->fFlags;
+        }
         cudaMemsetAsync(h->Vbuf[0], 0, sizeof(double) * (n + pad_rows) * k, h->stream);
         cudaMemsetAsync(h->Vbuf[1], 0, sizeof(double) * (n + pad_rows) * k, h->stream);
         cudaMemsetAsync(h->red, 0, sizeof(double) * (nk + kk2 + 2), h->stream);
-        cudaMemsetAsync(h->Gu_part, 0, sizeof(double) * h->uu_grid * kk2, h->stream);
+        cudaMemsetAsync(h->Gu_part, 0, sizeof(double) * std::max(h->uu_grid, h->fp.groups * kFExchWarps) * kk2, h->stream);
         e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) rc = fail(h, PRMF_ERR_CUDA, "init memset: %s", cudaGetErrorString(e));
     }

@@ -193,3 +193,37 @@ def test_standalone_objective_matches_oracle():
     for key in ("recon", "manifold", "ignore", "fro", "obj"):
         np.testing.assert_allclose(got[key], ref[key], rtol=1e-12)
     assert list(got) == ["recon", "manifold", "ignore", "fro", "gamma", "delta", "obj"]
+
+
+# ---- single-pass fused X kernel (opt-in, PRMF_FUSED=1): same results as the two-pass path ----------------
+@pytest.mark.parametrize("m,n,k,P", [
+    (64, 256, 6, 8),
+    (37, 131, 3, 5),
+    (5, 33, 1, 3),
+    (130, 1030, 7, 9),      # 3 gene panels
+    (200, 517, 10, 12),     # k = 10: two factors through the DFMA + butterfly path
+    (333, 2100, 9, 6),      # k = 9, 5 panels
+    (1000, 6750, 10, 20),   # the benchmark's gene count: 14 panels x 10 groups
+])
+def test_fused_kernel_matches_oracle(monkeypatch, m, n, k, P):
+    from prmf_b200 import nmf_manifold_vec_update
+    monkeypatch.setenv("PRMF_FUSED", "1")
+    X, nodelist, Gs, U, V, active = _instance(m, n, k, P, seed=m + n + k, weighted=True)
+    gamma, delta = 2.5, 0.3
+    Uo, Vo, parts_o, _, _, _ = oracle_block(X, U, V, Gs, nodelist, active, 3, gamma, delta)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        Ug, Vg, od = nmf_manifold_vec_update(X, U, V, Gs, active, n_steps=3, gamma=gamma, delta=delta,
+                                             nodelist=nodelist)
+    np.testing.assert_allclose(Ug, Uo, rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(Vg, Vo, rtol=1e-10, atol=1e-13)
+    for key, col in (("recon", 0), ("manifold", 1), ("ignore", 2), ("fro", 3), ("obj", 4)):
+        np.testing.assert_allclose(od[key], parts_o[-1, col], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("case", ["test1_norm", "small_planted"])
+def test_fused_whole_loop_matches_reference_fixture(monkeypatch, case):
+    monkeypatch.setenv("PRMF_FUSED", "1")
+    g = load_golden(case)
+    U, V, od, trace, _ = run_product(g)
+    check_run_against_golden(g, U, V, od, trace)

@@ -12,10 +12,11 @@
 // then forms the same U_blk (bitwise: fixed panel order) and continues with the outer-product accumulation from
 // the tile that is still in its shared memory.
 //
-// Inside a CTA (13 warps):
+// Inside a CTA (16 warps x 128 registers):
 //   warp 0        producer: TMA bulk copies of 8 row pieces + the 8 old U rows per stage into a ring
-//   warps 1..4    exchange: sum the consumer warps' partials, publish, wait for the other panels, U update
-//   warps 5..12   consumers: phase A on FP64 tensor cores (DMMA m8n8k4: 8 samples x 4 genes x 8 factors per
+//   warps 1..6    exchange (2 teams x 3 warps, one value per lane): sum the consumer warps' partials, publish
+//                 them as tagged words, collect the other panels' words, U update
+//   warps 8..15   consumers: phase A on FP64 tensor cores (DMMA m8n8k4: 8 samples x 4 genes x 8 factors per
 //                 instruction, so the reduction over genes happens in the accumulator fragment, no shuffles;
 //                 factors 8,9 by DFMA + one transposed butterfly), phase B by DFMA (thread owns 2 genes x k)
 // Phase B of block s-LAG is interleaved with phase A of block s so the exchange latency is off the critical path.
@@ -25,15 +26,18 @@
 namespace prmf {
 
 constexpr int kFConsWarps = 8;
-constexpr int kFExchWarps = 4;
-constexpr int kFThreads = (1 + kFExchWarps + kFConsWarps) * 32;   // 416
+constexpr int kFExParts = 3;       // the 80 values of a stage are split over 3 exchange warps (one value per lane)
+constexpr int kFExTeams = 2;       // teams of 3 exchange warps alternate over the stages
+constexpr int kFExchWarps = kFExParts * kFExTeams;
+constexpr int kFFirstCons = 8;     // warps 8..15 are the consumers (warp 0 producer, 1..6 exchange, 7 spare)
+constexpr int kFThreads = (kFFirstCons + kFConsWarps) * 32;      // 512 threads x 128 registers = the whole file
 constexpr int kFRS = 8;            // samples per stage (the DMMA M dimension)
 constexpr int kFKP = 10;           // factor pitch of the per-stage 8 x k blocks
 constexpr int kFExSlots = 16;      // exchange ring depth per row group (>= 2 x smem ring)
-constexpr int kFPaSlots = kFExchWarps;   // partial-sum buffers: one per exchange warp, so nobody waits on a barrier
+constexpr int kFPaSlots = kFExTeams;     // partial-sum buffers: one per exchange team, so nobody waits on a barrier
                                          // that can run two phases ahead
-constexpr int kFLag = 2;           // phase B runs this many stages behind phase A
-constexpr int kFMaxPanels = 32;
+constexpr int kFLag = 3;           // phase B runs this many stages behind phase A
+constexpr int kFMaxPanels = 16;    // gene panels per row group (n <= 8192)
 constexpr int kFMaxKSteps = 16;    // 4-gene DMMA steps per consumer warp (panel <= 512 genes)
 
 struct FusedParams {
@@ -47,10 +51,10 @@ struct FusedParams {
     int stages;                    // shared-memory ring depth (> kFLag + 1)
     uint32_t pitch;                // bytes between tile rows in shared memory (== 32 mod 128)
     double* Bpart;                 // [groups][n][k]
-    double* Gu_part;               // [groups * kFExchWarps][k*k]
-    double* Ex;                    // [groups][kFExSlots][panels][kFRS * kFKP]
-    unsigned long long* Flags;     // [groups][kFExSlots][panels]
-    unsigned long long epoch;      // flags of this launch are epoch + stage + 1
+    double* Gu_part;               // [groups][k*k]
+    unsigned long long* Ex;        // [groups][kFExSlots][panels][kFRS * kFKP][2]: {32 data bits | 32-bit tag} words
+    unsigned long long* Flags;     // unused (kept for layout compatibility)
+    unsigned long long epoch;      // tags of this launch are (uint32)(epoch + stage + 1)
 };
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
@@ -66,10 +70,20 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ double ld_cg_f64(const double* p) {
-    double v;
-    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
+// "LL" exchange words: an aligned 8-byte store is single-copy atomic, so a word that carries the expected tag also
+// carries valid data -- no fence and no separate flag round trip between producer and consumer CTAs.
+__device__ __forceinline__ void st_ll(unsigned long long* p, uint32_t data, uint32_t tag) {
+    const unsigned long long w = (unsigned long long)data | ((unsigned long long)tag << 32);
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ void st_ll2(unsigned long long* p, double v, uint32_t tag) {   // p 16-byte aligned
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long lo = (bits & 0xffffffffull) | ((unsigned long long)tag << 32);
+    const unsigned long long hi = (bits >> 32) | ((unsigned long long)tag << 32);
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(lo), "l"(hi) : "memory");
+}
+__device__ __forceinline__ void ld_ll2(const unsigned long long* p, unsigned long long& lo, unsigned long long& hi) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
 }
 
 // Transposed butterfly: every lane holds NV partial sums; afterwards the lane pair (l, l^1) holds the warp-wide sum
@@ -108,6 +122,17 @@ __device__ __forceinline__ int butterfly_index(int lane) {
     }
     return idx;
 }
+
+#ifdef PRMF_FUSED_TIMING
+__device__ unsigned long long g_fused_dbg[32];
+#define FT_DECL unsigned long long ft_t0 = clock64(), ft_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define FT_MARK(i) do { const unsigned long long now_ = clock64(); ft_acc[i] += now_ - ft_t0; ft_t0 = now_; } while (0)
+#define FT_DUMP(base, cond) do { if ((cond) && lane == 0) for (int i_ = 0; i_ < 8; ++i_) g_fused_dbg[(base) + i_] = ft_acc[i_]; } while (0)
+#else
+#define FT_DECL
+#define FT_MARK(i) do { } while (0)
+#define FT_DUMP(base, cond) do { } while (0)
+#endif
 
 template <int K>
 __global__ void __launch_bounds__(kFThreads, 1)
@@ -148,11 +173,11 @@ fused_xvu_kernel(const FusedParams p) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], kFConsWarps);
-            mbar_init(&un_bar[s], 1);
+            mbar_init(&un_bar[s], kFExParts);
         }
         for (int s = 0; s < kFPaSlots; ++s) {
             mbar_init(&pa_full[s], kFConsWarps);
-            mbar_init(&pa_empty[s], 1);
+            mbar_init(&pa_empty[s], kFExParts);
         }
         fence_mbar_init();
     }
@@ -185,113 +210,92 @@ fused_xvu_kernel(const FusedParams p) {
 
     // =================================== exchange warps ===================================
     if (warp <= kFExchWarps) {
-        const int ew = warp - 1;
+        const int team = (warp - 1) / kFExParts, part = (warp - 1) % kFExParts;
         constexpr int NV = kFRS * kFKP;                       // 80 values per stage
-        double gu[4] = {0.0, 0.0, 0.0, 0.0};                  // this lane's entries of U_new^T U_new (panel 0 only)
-        double* ex_base = p.Ex + (size_t)group * kFExSlots * p.panels * NV;
-        unsigned long long* fl_base = p.Flags + (size_t)group * kFExSlots * p.panels;
-        for (int s = ew; s < ns; s += kFExchWarps) {
-            const int pslot = s % kFPaSlots;                  // == ew
-            const uint32_t pph = (uint32_t)(s / kFPaSlots) & 1u;
-            mbar_wait(&pa_full[pslot], pph);
-            // CTA partial = sum of the consumer warps' partials (fixed order)
-            double mine[3];
+        const int idx = part * 32 + lane;                     // the value of this lane
+        const bool have = idx < NV;
+        const int r = idx / kFKP, c = idx - r * kFKP;
+        unsigned long long* ex_base = p.Ex + (size_t)group * kFExSlots * p.panels * NV * 2;
+        FT_DECL;
+        for (int s = team; s < ns; s += kFExTeams) {
+            const int pslot = s % kFPaSlots;                  // == team
+            FT_MARK(7);
+            mbar_wait(&pa_full[pslot], (uint32_t)(s / kFPaSlots) & 1u);
+            FT_MARK(0);
+            double mine = 0.0;                                // CTA partial = consumer warps' partials in order
+            if (have) {
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const int idx = lane + 32 * q;
-                double a = 0.0;
-                if (idx < NV) {
-#pragma unroll
-                    for (int w = 0; w < kFConsWarps; ++w) a += sPA[(pslot * kFConsWarps + w) * NV + idx];
-                }
-                mine[q] = a;
+                for (int w = 0; w < kFConsWarps; ++w) mine += sPA[(pslot * kFConsWarps + w) * NV + idx];
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&pa_empty[pslot]);
-            // publish
             const int xs = s % kFExSlots;
-            double* ex = ex_base + (size_t)xs * p.panels * NV;
+            unsigned long long* ex = ex_base + (size_t)xs * p.panels * NV * 2;
+            const uint32_t tag = (uint32_t)(p.epoch + (unsigned long long)s + 1ull);
+            if (have) st_ll2(ex + ((size_t)panel * NV + idx) * 2, mine, tag);
+            FT_MARK(1);
+            // A = sum over the panels in panel order (bitwise identical in every CTA of the group); one round of
+            // loads, words whose tag has not arrived yet are polled again
+            double A = 0.0;
+            if (have) {
+                double vals[kFMaxPanels];
+                uint32_t pending = 0;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const int idx = lane + 32 * q;
-                if (idx < NV) ex[(size_t)panel * NV + idx] = mine[q];
-            }
-            __threadfence();
-            __syncwarp();
-            const unsigned long long want = p.epoch + (unsigned long long)s + 1ull;
-            if (lane == 0) st_release_u64(&fl_base[(size_t)xs * p.panels + panel], want);
-            // wait for every panel of the group
-            if (lane < p.panels) {
-                const unsigned long long* f = &fl_base[(size_t)xs * p.panels + lane];
-                while (ld_acquire_u64(f) < want) { }
-            }
-            __syncwarp();
-            // A = sum over panels in panel order (identical in every CTA of the group)
-            double A[3];
+                for (int pp = 0; pp < kFMaxPanels; ++pp) {
+                    vals[pp] = 0.0;
+                    if (pp < p.panels && pp != panel) pending |= 1u << pp;
+                }
+                while (pending) {
+                    unsigned long long lo[kFMaxPanels], hi[kFMaxPanels];
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const int idx = lane + 32 * q;
-                double a = 0.0;
-                if (idx < NV)
-                    for (int pp = 0; pp < p.panels; ++pp) a += (pp == panel) ? mine[q] : ld_cg_f64(ex + (size_t)pp * NV + idx);
-                A[q] = a;
+                    for (int pp = 0; pp < kFMaxPanels; ++pp)
+                        if (pending & (1u << pp)) ld_ll2(ex + ((size_t)pp * NV + idx) * 2, lo[pp], hi[pp]);
+#pragma unroll
+                    for (int pp = 0; pp < kFMaxPanels; ++pp)
+                        if (pending & (1u << pp)) {
+                            if ((uint32_t)(lo[pp] >> 32) == tag && (uint32_t)(hi[pp] >> 32) == tag) {
+                                vals[pp] = __longlong_as_double((long long)((lo[pp] & 0xffffffffull) | (hi[pp] << 32)));
+                                pending &= ~(1u << pp);
+                            }
+                        }
+                }
+#pragma unroll
+                for (int pp = 0; pp < kFMaxPanels; ++pp)
+                    if (pp < p.panels) A += (pp == panel) ? mine : vals[pp];
             }
-            // U update of the 8 rows (:421-422)
+            FT_MARK(2);
+            // U update of this lane's entry (:421-422)
             const int slot = s % S;
             mbar_wait(&full_bar[slot], (uint32_t)(s / S) & 1u);          // the old U rows travelled with the tile
             const double* uold = reinterpret_cast<const double*>(sm_stage + (size_t)slot * stage_bytes + x_stage_bytes);
             double* un = sUn + (size_t)slot * NV;
             const int64_t r0 = rbeg + (int64_t)s * kFRS;
+            if (have) {
+                double v = 0.0;
+                if (c < K) {
+                    const double* ur = uold + r * K;
+                    double den = 0.0;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const int idx = lane + 32 * q;
-                if (idx < NV) {
-                    const int r = idx / kFKP, c = idx - r * kFKP;
-                    double v = 0.0;
-                    if (c < K) {
-                        const double* ur = uold + r * K;
-                        double den = 0.0;
-#pragma unroll
-                        for (int l = 0; l < K; ++l) den = fma(ur[l], sGv[l * K + c], den);
-                        const double u = ur[c];
-                        den += u;
-                        const double f = (den != 0.0) ? A[q] / den : 1.0;
-                        v = u * f;
-                        if (panel == 0 && r0 + r < p.m) p.Unew[(r0 + r) * K + c] = v;
-                    }
-                    un[idx] = v;
+                    for (int l = 0; l < K; ++l) den = fma(ur[l], sGv[l * K + c], den);
+                    const double u = ur[c];
+                    den += u;
+                    const double f = (den != 0.0) ? A / den : 1.0;
+                    v = u * f;
+                    if (panel == 0 && r0 + r < p.m) p.Unew[(r0 + r) * K + c] = v;
                 }
-            }
-            __syncwarp();
-            if (panel == 0) {
-                const int rows = (int)min((int64_t)kFRS, rend - r0);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int e = lane + 32 * q;
-                    if (e < K * K) {
-                        const int a = e / K, b = e - a * K;
-                        double g = gu[q];
-                        for (int r = 0; r < rows; ++r) g = fma(un[r * kFKP + a], un[r * kFKP + b], g);
-                        gu[q] = g;
-                    }
-                }
+                un[idx] = v;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&un_bar[slot]);
+            FT_MARK(3);
         }
-        if (panel == 0) {
-            double* out = p.Gu_part + ((size_t)group * kFExchWarps + ew) * K * K;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int e = lane + 32 * q;
-                if (e < K * K) out[e] = gu[q];
-            }
-        }
+        FT_DUMP(0, panel == 0 && group == 0 && warp == 1);
         return;
     }
+    if (warp < kFFirstCons) return;                           // spare warp
 
     // =================================== consumer warps ===================================
-    const int cw = warp - 1 - kFExchWarps;                   // 0..7
+    const int cw = warp - kFFirstCons;                       // 0..7
     const int t = cw * 32 + lane;                            // 0..255: owns double2 column t (genes c0+2t, c0+2t+1)
     const int H2 = p.panel_w >> 1;                           // double2 columns in the panel
     const bool own = t < H2;
@@ -319,29 +323,35 @@ fused_xvu_kernel(const FusedParams p) {
     for (int g = 0; g < 2; ++g)
 #pragma unroll
         for (int c = 0; c < K; ++c) acc[g][c] = 0.0;
+    double gu = 0.0;
 
+    FT_DECL;
     for (int s = 0; s < ns + kFLag; ++s) {
+        FT_MARK(7);
         if (s < ns) {
             // ---------------- phase A of stage s ----------------
             const int slot = s % S;
             mbar_wait(&full_bar[slot], (uint32_t)(s / S) & 1u);
+            FT_MARK(0);
             const unsigned char* tile = sm_stage + (size_t)slot * stage_bytes;
             const int pslot = s % kFPaSlots;
             mbar_wait(&pa_empty[pslot], ((uint32_t)(s / kFPaSlots) & 1u) ^ 1u);
-            double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;  // two accumulator chains
-            const unsigned char* arow_ptr = tile + (size_t)arow * p.pitch + ((size_t)(4 * ks0 + acol) << 3);
+            FT_MARK(1);
+            // 8 independent accumulator chains of 2 DMMAs: a dependent DMMA has a latency of a few hundred cycles
+            constexpr int NCH = 8;
+            double dch[NCH][2];
 #pragma unroll
-            for (int j = 0; j < kFMaxKSteps; j += 2) {
-                if (j < ks_per_warp) {
-                    const double a = *reinterpret_cast<const double*>(arow_ptr + (size_t)j * 32);
-                    dmma884(d0, d1, a, bfrag[j]);
-                }
-                if (j + 1 < ks_per_warp) {
-                    const double a = *reinterpret_cast<const double*>(arow_ptr + (size_t)(j + 1) * 32);
-                    dmma884(e0, e1, a, bfrag[j + 1]);
-                }
-            }
-            d0 += e0; d1 += e1;
+            for (int ch = 0; ch < NCH; ++ch) { dch[ch][0] = 0.0; dch[ch][1] = 0.0; }
+            const unsigned char* arow_ptr = tile + (size_t)arow * p.pitch + ((size_t)(4 * ks0 + acol) << 3);
+            double afrag[kFMaxKSteps];
+#pragma unroll
+            for (int j = 0; j < kFMaxKSteps; ++j)
+                afrag[j] = (j < ks_per_warp) ? *reinterpret_cast<const double*>(arow_ptr + (size_t)j * 32) : 0.0;
+#pragma unroll
+            for (int j = 0; j < kFMaxKSteps; ++j)
+                if (j < ks_per_warp) dmma884(dch[j % NCH][0], dch[j % NCH][1], afrag[j], bfrag[j]);
+            double d0 = ((dch[0][0] + dch[1][0]) + (dch[2][0] + dch[3][0])) + ((dch[4][0] + dch[5][0]) + (dch[6][0] + dch[7][0]));
+            double d1 = ((dch[0][1] + dch[1][1]) + (dch[2][1] + dch[3][1])) + ((dch[4][1] + dch[5][1]) + (dch[6][1] + dch[7][1]));
             double* pa = sPA + (size_t)(pslot * kFConsWarps + cw) * (kFRS * kFKP);
             {   // D fragment: D[row = lane/4][col = 2*(lane%4) + {0,1}]
                 const int col = 2 * acol;
@@ -366,30 +376,46 @@ fused_xvu_kernel(const FusedParams p) {
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&pa_full[pslot]);
+            FT_MARK(2);
         }
         if (s >= kFLag) {
             // ---------------- phase B of stage s - LAG ----------------
             const int sb = s - kFLag;
             const int slot = sb % S;
             mbar_wait(&un_bar[slot], (uint32_t)(sb / S) & 1u);
+            FT_MARK(3);
             const unsigned char* tile = sm_stage + (size_t)slot * stage_bytes;
             const double* un = sUn + (size_t)slot * (kFRS * kFKP);
             if (own) {
 #pragma unroll
                 for (int r = 0; r < kFRS; ++r) {
                     const double2 x = *reinterpret_cast<const double2*>(tile + (size_t)r * p.pitch + ((size_t)t << 4));
+                    const double2* u2 = reinterpret_cast<const double2*>(un + r * kFKP);     // 80-byte rows: 16-byte aligned
 #pragma unroll
-                    for (int c = 0; c < K; ++c) {
-                        const double u = un[r * kFKP + c];
-                        acc[0][c] = fma(x.x, u, acc[0][c]);
-                        acc[1][c] = fma(x.y, u, acc[1][c]);
+                    for (int c2 = 0; c2 < (K + 1) / 2; ++c2) {
+                        const double2 u = u2[c2];
+                        acc[0][2 * c2] = fma(x.x, u.x, acc[0][2 * c2]);
+                        acc[1][2 * c2] = fma(x.y, u.x, acc[1][2 * c2]);
+                        if (2 * c2 + 1 < K) {
+                            acc[0][2 * c2 + 1] = fma(x.x, u.y, acc[0][2 * c2 + 1]);
+                            acc[1][2 * c2 + 1] = fma(x.y, u.y, acc[1][2 * c2 + 1]);
+                        }
                     }
                 }
             }
+            if (panel == 0 && t < K * K) {                    // U_new^T U_new (:425): one entry per thread
+                const int ga = t / K, gb = t - ga * K;
+                const int rows = (int)min((int64_t)kFRS, rend - (rbeg + (int64_t)sb * kFRS));
+                for (int r = 0; r < rows; ++r) gu = fma(un[r * kFKP + ga], un[r * kFKP + gb], gu);
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[slot]);
+            FT_MARK(4);
         }
     }
+    FT_DUMP(8, panel == 0 && group == 0 && cw == 0);
+    FT_DUMP(16, panel == 5 && group == 3 && cw == 3);
+    if (panel == 0 && t < K * K) p.Gu_part[(size_t)group * K * K + t] = gu;
     if (own) {
 #pragma unroll
         for (int g = 0; g < 2; ++g) {

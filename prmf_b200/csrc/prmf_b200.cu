@@ -117,8 +117,8 @@ struct prmf_handle {
     bool use_fused = false;
     FusedParams fp{};
     size_t fused_smem = 0;
-    double *U2 = nullptr, *fEx = nullptr;
-    unsigned long long* fFlags = nullptr;
+    double* U2 = nullptr;
+    unsigned long long* fEx = nullptr;        // tagged exchange words of the fused kernel
     unsigned long long fused_epoch = 0;
 
     // multi-GPU
@@ -290,7 +290,7 @@ int launch_fused_t(prmf_handle* h) {
 int launch_fused(prmf_handle* h) {
     if (h->m == 0) {
         CU(cudaMemsetAsync(h->Bpart, 0, sizeof(double) * h->fp.groups * h->n * h->k, h->stream));
-        CU(cudaMemsetAsync(h->Gu_part, 0, sizeof(double) * h->fp.groups * kFExchWarps * h->k * h->k, h->stream));
+        CU(cudaMemsetAsync(h->Gu_part, 0, sizeof(double) * h->fp.groups * h->k * h->k, h->stream));
         return PRMF_OK;
     }
     h->fused_epoch += (1ull << 24);
@@ -422,7 +422,7 @@ int launch_v_update_objective(prmf_handle* h, bool sharded, double tradeoff) {
     const double* Bsrc = sharded ? h->red : h->Bpart;
     const int bchunks = sharded ? 1 : h->use_fused ? h->fp.groups : (h->use_tma ? h->tchunks : h->chunks);
     const double* Gusrc = sharded ? h->red + nk : h->Gu_part;
-    const int gchunks = sharded ? 1 : h->use_fused ? h->fp.groups * kFExchWarps : h->uu_grid;
+    const int gchunks = sharded ? 1 : h->use_fused ? h->fp.groups : h->uu_grid;
     NI_SWITCH(h->ni, (v_update_objective_kernel<NI><<<h->vu_grid, kTailThreads, vu_smem(h), h->stream>>>(
                          h->Vbuf[h->vcur], h->Vbuf[h->vcur ^ 1], Bsrc, bchunks, nk, Gusrc, gchunks, (int)h->n, h->k, h->pw,
                          h->active, h->pos, h->gd, h->vu_rows, h->Gv_part, h->VB_part, h->normX_sq, h->as, h->Gv,
@@ -573,7 +573,7 @@ int enqueue_steps(prmf_handle* h, int n_steps, double gamma, double delta, doubl
             double* dst = h->p2p_ready ? h->p2p_buf + (size_t)h->p2p_parity * h->p2p_red_count : h->red;
             reduce_pack_kernel<<<(unsigned)((nk + kk2 + 2 + 255) / 256), 256, 0, h->stream>>>(
                 h->Bpart, h->use_fused ? h->fp.groups : (h->use_tma ? h->tchunks : h->chunks), nk, h->Gu_part,
-                h->use_fused ? h->fp.groups * kFExchWarps : h->uu_grid, h->k, dst);
+                h->use_fused ? h->fp.groups : h->uu_grid, h->k, dst);
             LAUNCH_CHECK("reduce_pack_kernel");
             if (!h->p2p_ready) rc = allreduce(h, h->red, red_count);      // else: summed inside the V update
             toc();
@@ -719,7 +719,7 @@ int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global
     // single-pass fused kernel plan (opt-in)
     {
         const char* ef = getenv("PRMF_FUSED");
-        h->use_fused = ef && atoi(ef) == 1 && k <= 10 && n <= 512 * kFMaxPanels;
+        h->use_fused = ef && atoi(ef) == 1 && k <= 10 && n <= 512 * kFMaxPanels;     // tags: epoch starts at 2^24 > 0
         if (h->use_fused) {
             FusedParams& f = h->fp;
             f.panels = (int)((n + 511) / 512);
@@ -752,11 +752,10 @@ int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global
         size_t total = 0;
         total += 3 * pad((size_t)(m_local + pad_rows) * k, d);                                      // U, U2, Ub
         if (h->use_fused)
-            total += pad((size_t)h->fp.groups * kFExSlots * h->fp.panels * kFRS * kFKP, d) +
-                     pad((size_t)h->fp.groups * kFExSlots * h->fp.panels, sizeof(unsigned long long));
+            total += pad((size_t)h->fp.groups * kFExSlots * h->fp.panels * kFRS * kFKP * 2, sizeof(unsigned long long));
         total += pad((size_t)std::max(h->chunks1, h->tchunks1) * std::max<int64_t>(1, m_local) * k, d);   // Apart
         total += 2 * pad((size_t)(n + pad_rows) * k, d) + pad((size_t)nk, d);                      // Vbuf[2], Vb
-        total += 2 * pad(kk2, d) + pad((size_t)std::max(h->uu_grid, h->fp.groups * kFExchWarps) * kk2, d) + pad((size_t)h->vu_grid * kk2, d);
+        total += 2 * pad(kk2, d) + pad((size_t)std::max(h->uu_grid, h->fp.groups) * kk2, d) + pad((size_t)h->vu_grid * kk2, d);
         total += pad(h->vu_grid, d) + pad((size_t)std::max({h->chunks, h->tchunks, h->fp.groups}) * nk, d);   // VB_part, Bpart
         total += pad((size_t)nk + kk2 + 2, d) + pad(1, d) + pad((size_t)h->sm_count * 8, d) + pad(2, d);
         total += pad(1, sizeof(int)) + pad(1, sizeof(unsigned int)) + pad(k, sizeof(int32_t)) + pad(nk, sizeof(int32_t));
@@ -773,13 +772,12 @@ int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global
     TAKE(h->Ub, double, (m_local + pad_rows) * k);
     TAKE(h->U2, double, (m_local + pad_rows) * k);
     if (h->use_fused) {
-        TAKE(h->fEx, double, (size_t)h->fp.groups * kFExSlots * h->fp.panels * kFRS * kFKP);
-        TAKE(h->fFlags, unsigned long long, (size_t)h->fp.groups * kFExSlots * h->fp.panels);
+        TAKE(h->fEx, unsigned long long, (size_t)h->fp.groups * kFExSlots * h->fp.panels * kFRS * kFKP * 2);
     }
     TAKE(h->Apart, double, (size_t)std::max(h->chunks1, h->tchunks1) * std::max<int64_t>(1, m_local) * k);
     TAKE(h->Vbuf[0], double, (n + pad_rows) * k); TAKE(h->Vbuf[1], double, (n + pad_rows) * k); TAKE(h->Vb, double, nk);
     TAKE(h->Gv, double, kk2); TAKE(h->Gvb, double, kk2);
-    TAKE(h->Gu_part, double, (size_t)std::max(h->uu_grid, h->fp.groups * kFExchWarps) * kk2);
+    TAKE(h->Gu_part, double, (size_t)std::max(h->uu_grid, h->fp.groups) * kk2);
     TAKE(h->Gv_part, double, (size_t)h->vu_grid * kk2);
     TAKE(h->VB_part, double, h->vu_grid);
     TAKE(h->Bpart, double, (size_t)std::max({h->chunks, h->tchunks, h->fp.groups}) * nk);
@@ -800,14 +798,14 @@ int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global
         cudaMemsetAsync(h->U, 0, sizeof(double) * (m_local + pad_rows) * k, h->stream);
         cudaMemsetAsync(h->U2, 0, sizeof(double) * (m_local + pad_rows) * k, h->stream);
         if (h->use_fused) {
-            cudaMemsetAsync(h->fFlags, 0, sizeof(unsigned long long) * h->fp.groups * kFExSlots * h->fp.panels, h->stream);
+            cudaMemsetAsync(h->fEx, 0, sizeof(unsigned long long) * h->fp.groups * kFExSlots * h->fp.panels * kFRS * kFKP * 2, h->stream);
             h->fp.X = h->X; h->fp.Gv = h->Gv; h->fp.Bpart = h->Bpart; h->fp.Gu_part = h->Gu_part;
-            h->fp.Ex = h->fEx; h->fp.Flags = h->fFlags;
+            h->fp.Ex = h->fEx; h->fp.Flags = nullptr;
         }
         cudaMemsetAsync(h->Vbuf[0], 0, sizeof(double) * (n + pad_rows) * k, h->stream);
         cudaMemsetAsync(h->Vbuf[1], 0, sizeof(double) * (n + pad_rows) * k, h->stream);
         cudaMemsetAsync(h->red, 0, sizeof(double) * (nk + kk2 + 2), h->stream);
-        cudaMemsetAsync(h->Gu_part, 0, sizeof(double) * std::max(h->uu_grid, h->fp.groups * kFExchWarps) * kk2, h->stream);
+        cudaMemsetAsync(h->Gu_part, 0, sizeof(double) * std::max(h->uu_grid, h->fp.groups) * kk2, h->stream);
         e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) rc = fail(h, PRMF_ERR_CUDA, "init memset: %s", cudaGetErrorString(e));
     }
@@ -1210,6 +1208,12 @@ int prmf_kernel_times(prmf_handle* h, int reset, double* phase_ms, int64_t* phas
 }
 
 void* prmf_stream(const prmf_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+#ifdef PRMF_FUSED_TIMING
+int prmf_debug_fused(unsigned long long* out32) {
+    return cudaMemcpyFromSymbol(out32, g_fused_dbg, sizeof(unsigned long long) * 32) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 #ifdef PRMF_TAIL_TIMING
 int prmf_debug_tail_stamps(unsigned long long* out16) {

@@ -49,6 +49,17 @@ int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global
                 void* stream);
 int prmf_destroy(prmf_handle* h);
 
+/* Storage / arithmetic mode of the X streams.  PRMF_X_F64 (prmf_create) is the parity mode: X in fp64, DFMA.
+ * PRMF_X_TF32 (opt-in; BASELINE config 5, "dense-enough contraction for the tensor-core path") keeps X and X^T
+ * in HBM as fp32 rounded to tf32 and runs X.V (:420) and X^T.U (:424) on the tcgen05 tensor cores with fp32
+ * accumulation in TMEM; U, V, the updates, the objective and the reductions over ranks stay fp64.  Not bit-parity
+ * with the reference: the tests state its tolerance. */
+#define PRMF_X_F64  0
+#define PRMF_X_TF32 1
+int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_global, int64_t n, int k,
+                   void* stream, int x_dtype);
+int prmf_x_dtype(const prmf_handle* h);
+
 /* Last error text of `h` (or of the last failed prmf_create when h is NULL). */
 const char* prmf_last_error(const prmf_handle* h);
 
@@ -57,6 +68,9 @@ const char* prmf_last_error(const prmf_handle* h);
  * layout on the handle's stream).  X argument of nmf_pathway / nmf_manifold_vec_update (:556,:374). */
 int prmf_set_X(prmf_handle* h, const double* X_host, int64_t ld);
 int prmf_set_X_device(prmf_handle* h, const double* X_dev, int64_t ld);
+/* PRMF_X_TF32 handles only: fp32 source (host pointer, or device pointer when on_device != 0), `ld` floats
+ * between rows; the fp64 entry points above also work in that mode (the values are rounded on the device). */
+int prmf_set_X_f32(prmf_handle* h, const float* X, int64_t ld, int on_device);
 
 /* Global ||X||_F^2 (all-reduced when a communicator is attached); `np.linalg.norm(X)` at :640. */
 int prmf_get_normX_sq(prmf_handle* h, double* out);

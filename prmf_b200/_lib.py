@@ -10,6 +10,7 @@ OBJ_STRIDE = 8
 UNIQUE_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64
 N_PHASES = 6
+X_DTYPES = {"f64": 0, "tf32": 1}          # PRMF_X_F64 / PRMF_X_TF32
 PHASES = ("xv", "u_update", "xtu", "reduce", "v_update", "objective")
 
 # every symbol include/prmf_b200.h declares: name -> (restype, argtypes)
@@ -17,10 +18,13 @@ _P = c_void_p
 SYMBOLS = {
     "prmf_abi_version": (c_int, []),
     "prmf_create": (c_int, [POINTER(_P), c_int, c_int64, c_int64, c_int64, c_int, _P]),
+    "prmf_create_ex": (c_int, [POINTER(_P), c_int, c_int64, c_int64, c_int64, c_int, _P, c_int]),
+    "prmf_x_dtype": (c_int, [_P]),
     "prmf_destroy": (c_int, [_P]),
     "prmf_last_error": (c_char_p, [_P]),
     "prmf_set_X": (c_int, [_P, _P, c_int64]),
     "prmf_set_X_device": (c_int, [_P, _P, c_int64]),
+    "prmf_set_X_f32": (c_int, [_P, _P, c_int64, c_int]),
     "prmf_get_normX_sq": (c_int, [_P, POINTER(c_double)]),
     "prmf_set_pathways": (c_int, [_P, c_int32, _P, _P, _P, _P, _P]),
     "prmf_set_UV": (c_int, [_P, _P, _P]),

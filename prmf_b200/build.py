@@ -12,7 +12,7 @@ LIB = os.path.join(HERE, "libprmf_b200.so")
 HEADER = os.path.join(HERE, "..", "include", "prmf_b200.h")
 # translation unit -> headers it depends on
 SOURCES = {
-    "prmf_b200.cu": ["kernels.cuh", "fused.cuh", "nccl_dyn.h"],
+    "prmf_b200.cu": ["kernels.cuh", "fused.cuh", "tf32.cuh", "nccl_dyn.h"],
     "preprocess.cu": [],
 }
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -21,6 +21,7 @@
 
 #include "kernels.cuh"
 #include "fused.cuh"
+#include "tf32.cuh"
 #include "nccl_dyn.h"
 
 using namespace prmf;
@@ -120,6 +121,17 @@ struct prmf_handle {
     double* U2 = nullptr;
     unsigned long long* fEx = nullptr;        // tagged exchange words of the fused kernel
     unsigned long long fused_epoch = 0;
+
+    // TF32 tensor-core storage mode (opt-in: prmf_create_ex with PRMF_X_TF32): X, X^T kept as fp32 rounded to tf32,
+    // both passes by tc_rowdot_kernel, everything else unchanged
+    bool x_tf32 = false;
+    float *X32 = nullptr, *Xt32 = nullptr, *Vt32 = nullptr, *Ut32 = nullptr;
+    int64_t ldx32 = 0, ldxt32 = 0;
+    int Kp = 0;
+    CUtensorMap tm_X{}, tm_Xt{}, tm_Vt{}, tm_Ut{};
+    TcParams tc1{}, tc2{};                    // pass 1: M = X (m x n), W = V^T; pass 2: M = X^T (n x m), W = U^T
+    int tc_tiles1 = 0, tc_chunks1 = 0, tc_tiles2 = 0, tc_chunks2 = 0;
+    size_t tc_smem = 0;
 
     // multi-GPU
     NcclComm comm = nullptr;
@@ -306,9 +318,34 @@ int launch_fused(prmf_handle* h) {
     return PRMF_OK;
 }
 
+// number of per-chunk partials the passes leave in Apart / Bpart
+int a_chunks(const prmf_handle* h) { return h->x_tf32 ? h->tc_chunks1 : h->use_tma ? h->tchunks1 : h->chunks1; }
+int b_chunks(const prmf_handle* h) {
+    return h->x_tf32 ? h->tc_chunks2 : h->use_fused ? h->fp.groups : h->use_tma ? h->tchunks : h->chunks;
+}
+
+// TF32 mode: one tensor-core kernel serves both passes
+int launch_tc(prmf_handle* h, const CUtensorMap& tmM, const CUtensorMap& tmW, const TcParams& prm, int tiles, int chunks,
+              const char* name) {
+    dim3 grid(tiles, chunks);
+    tc_rowdot_kernel<<<grid, kTcThreads, h->tc_smem, h->stream>>>(tmM, tmW, prm);
+    LAUNCH_CHECK(name);
+    return PRMF_OK;
+}
+
+// W^T operand of the tensor-core passes: Wt[f][r] = tf32(W[r][f])
+int refresh_wt(prmf_handle* h, const double* W, int64_t rows, float* Wt, int64_t ld) {
+    if (rows == 0) return PRMF_OK;
+    dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((h->Kp + 31) / 32));
+    cast_transpose_w_kernel<<<grid, 256, 0, h->stream>>>(W, rows, h->k, h->Kp, Wt, ld);
+    LAUNCH_CHECK("cast_transpose_w_kernel");
+    return PRMF_OK;
+}
+
 // pass 1: A partials = Xt^T . V   (M = Xt: n rows x m cols)
 int launch_xv(prmf_handle* h) {
     if (h->m == 0) return PRMF_OK;
+    if (h->x_tf32) return launch_tc(h, h->tm_X, h->tm_Vt, h->tc1, h->tc_tiles1, h->tc_chunks1, "tc_rowdot_kernel(pass 1)");
     if (h->use_tma) {
         int rc = 0;
         if (h->k > 10) {
@@ -334,8 +371,14 @@ int launch_xv(prmf_handle* h) {
 // pass 2: B partials = X^T . U_new   (M = X: m rows x n cols)
 int launch_xtu(prmf_handle* h) {
     if (h->m == 0) {
-        CU(cudaMemsetAsync(h->Bpart, 0, sizeof(double) * std::max(h->chunks, h->tchunks) * h->n * h->k, h->stream));
+        CU(cudaMemsetAsync(h->Bpart, 0, sizeof(double) * std::max({h->chunks, h->tchunks, h->tc_chunks2}) * h->n * h->k,
+                           h->stream));
         return PRMF_OK;
+    }
+    if (h->x_tf32) {
+        int rc = refresh_wt(h, h->U, h->m, h->Ut32, h->ldxt32);
+        if (rc) return rc;
+        return launch_tc(h, h->tm_Xt, h->tm_Ut, h->tc2, h->tc_tiles2, h->tc_chunks2, "tc_rowdot_kernel(pass 2)");
     }
     if (h->use_tma) {
         int rc = 0;
@@ -398,7 +441,7 @@ int launch_u_update(prmf_handle* h) {
         return PRMF_OK;
     }
     NI_SWITCH(h->ni, (u_update_kernel<NI><<<h->uu_grid, kTailThreads, uu_smem(h), h->stream>>>(
-                         h->U, h->Apart, h->use_tma ? h->tchunks1 : h->chunks1, h->Gv, h->m, h->k, h->uu_rows, h->Gu_part)));
+                         h->U, h->Apart, a_chunks(h), h->Gv, h->m, h->k, h->uu_rows, h->Gu_part)));
     LAUNCH_CHECK("u_update_kernel");
     return PRMF_OK;
 }
@@ -420,7 +463,7 @@ int launch_v_update_objective(prmf_handle* h, bool sharded, double tradeoff) {
         h->p2p_parity ^= 1;
     }
     const double* Bsrc = sharded ? h->red : h->Bpart;
-    const int bchunks = sharded ? 1 : h->use_fused ? h->fp.groups : (h->use_tma ? h->tchunks : h->chunks);
+    const int bchunks = sharded ? 1 : b_chunks(h);
     const double* Gusrc = sharded ? h->red + nk : h->Gu_part;
     const int gchunks = sharded ? 1 : h->use_fused ? h->fp.groups : h->uu_grid;
     NI_SWITCH(h->ni, (v_update_objective_kernel<NI><<<h->vu_grid, kTailThreads, vu_smem(h), h->stream>>>(
@@ -429,6 +472,7 @@ int launch_v_update_objective(prmf_handle* h, bool sharded, double tradeoff) {
                          tradeoff, h->obj, h->step_counter, h->obj_capacity, h->ticket, px)));
     LAUNCH_CHECK("v_update_objective_kernel");
     h->vcur ^= 1;
+    if (h->x_tf32) return refresh_wt(h, h->Vbuf[h->vcur], h->n, h->Vt32, h->ldx32);
     return PRMF_OK;
 }
 
@@ -572,7 +616,7 @@ int enqueue_steps(prmf_handle* h, int n_steps, double gamma, double delta, doubl
             tic(3);
             double* dst = h->p2p_ready ? h->p2p_buf + (size_t)h->p2p_parity * h->p2p_red_count : h->red;
             reduce_pack_kernel<<<(unsigned)((nk + kk2 + 2 + 255) / 256), 256, 0, h->stream>>>(
-                h->Bpart, h->use_fused ? h->fp.groups : (h->use_tma ? h->tchunks : h->chunks), nk, h->Gu_part,
+                h->Bpart, b_chunks(h), nk, h->Gu_part,
                 h->use_fused ? h->fp.groups : h->uu_grid, h->k, dst);
             LAUNCH_CHECK("reduce_pack_kernel");
             if (!h->p2p_ready) rc = allreduce(h, h->red, red_count);      // else: summed inside the V update
@@ -597,10 +641,133 @@ int collect(prmf_handle* h, int n_steps, double* obj_parts, double* gamma_delta_
     return PRMF_OK;
 }
 
+// ---- TF32 mode set-up ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D fp32 tensor map over a row-major matrix (rows x cols, leading dimension ld), box = box_rows x 32 columns,
+// 128-byte swizzle; out-of-range elements read as zero (ragged tiles need no special case).
+int make_tensor_map(prmf_handle* h, CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld,
+                    int box_rows) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+            return fail(h, PRMF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+        encode = (EncodeTiledFn)fn;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)kTcBlockK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, PRMF_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return PRMF_OK;
+}
+
+// Tiles of 128 rows x column chunks: pick the smallest chunk count whose wave quantisation over the
+// 2 x SM-count resident CTAs is within 3 % of the best one.
+void plan_tc(const prmf_handle* h, int64_t R, int64_t C, int* tiles, int* chunks, int64_t* cols_per_chunk) {
+    *tiles = (int)std::max<int64_t>(1, (R + kTcTileRows - 1) / kTcTileRows);
+    const double slots = 2.0 * h->sm_count;
+    const int max_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(64, C / 512));
+    double best = 0.0;
+    std::vector<double> eff(max_chunks + 1, 0.0);
+    for (int c = 1; c <= max_chunks; ++c) {
+        const double ctas = (double)*tiles * c;
+        eff[c] = ctas / (std::ceil(ctas / slots) * slots);
+        best = std::max(best, eff[c]);
+    }
+    int pick = 1;
+    for (int c = 1; c <= max_chunks; ++c)
+        if (eff[c] >= best - 0.03) { pick = c; break; }
+    *cols_per_chunk = round_up(std::max<int64_t>(1, (C + pick - 1) / pick), kTcBlockK);
+    *chunks = (int)std::max<int64_t>(1, (C + *cols_per_chunk - 1) / *cols_per_chunk);
+}
+
+int setup_tf32(prmf_handle* h) {
+    const int k = h->k;
+    h->Kp = (int)round_up(k, 16);
+    h->ldx32 = round_up(h->n, 32);
+    h->ldxt32 = round_up(std::max<int64_t>(1, h->m), 32);
+    int64_t cpc1 = 0, cpc2 = 0;
+    plan_tc(h, h->m, h->n, &h->tc_tiles1, &h->tc_chunks1, &cpc1);
+    plan_tc(h, h->n, h->m, &h->tc_tiles2, &h->tc_chunks2, &cpc2);
+    const size_t stage = (size_t)kTcTileRows * kTcBlockK * 4 + (size_t)h->Kp * kTcBlockK * 4;
+    int stages = (int)((108 * 1024) / stage);                      // two CTAs per SM
+    stages = std::max(2, std::min(8, stages));
+    h->tc_smem = (size_t)stages * stage + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
+    uint32_t tcols = 32;
+    while ((int)tcols < h->Kp) tcols <<= 1;
+    h->tc1 = TcParams{h->m, h->n, k, h->Kp, cpc1, stages, tcols, nullptr};
+    h->tc2 = TcParams{h->n, h->m, k, h->Kp, cpc2, stages, tcols, nullptr};
+    return PRMF_OK;
+}
+
+int finish_setup_tf32(prmf_handle* h) {
+    h->tc1.Out = h->Apart;
+    h->tc2.Out = h->Bpart;
+    CU(cudaFuncSetAttribute(tc_rowdot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tc_smem));
+    CU(cudaFuncSetAttribute(tc_rowdot_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int rc = 0;
+    if (h->m > 0) {
+        if ((rc = make_tensor_map(h, &h->tm_X, h->X32, h->m, h->n, h->ldx32, kTcTileRows))) return rc;
+        if ((rc = make_tensor_map(h, &h->tm_Xt, h->Xt32, h->n, h->m, h->ldxt32, kTcTileRows))) return rc;
+        if ((rc = make_tensor_map(h, &h->tm_Ut, h->Ut32, h->Kp, h->m, h->ldxt32, h->Kp))) return rc;
+        if ((rc = make_tensor_map(h, &h->tm_Vt, h->Vt32, h->Kp, h->n, h->ldx32, h->Kp))) return rc;
+    }
+    return PRMF_OK;
+}
+
+// TF32 mode: round a row block (host or device, fp64 or fp32) to tf32 into the fp32 layout.  Host blocks go
+// through a bounded device staging buffer, block after block on the handle's stream.
+template <typename T>
+int store_tf32(prmf_handle* h, const T* X, int64_t ld, bool on_host) {
+    const int64_t m = h->m, n = h->n;
+    if (m == 0) return PRMF_OK;
+    const int grid = h->sm_count * 8;
+    if (!on_host) {
+        to_tf32_rows_kernel<T><<<grid, 256, 0, h->stream>>>(X, ld, m, n, h->X32, h->ldx32);
+        LAUNCH_CHECK("to_tf32_rows_kernel");
+        return PRMF_OK;
+    }
+    const int64_t rows_blk = std::max<int64_t>(1, std::min<int64_t>(m, ((int64_t)256 << 20) / (n * (int64_t)sizeof(T))));
+    T* stage = nullptr;
+    int rc = dalloc(h, &stage, (size_t)rows_blk * n);
+    if (rc) return rc;
+    cudaError_t e = cudaSuccess;
+    for (int64_t r0 = 0; r0 < m && e == cudaSuccess; r0 += rows_blk) {
+        const int64_t rows = std::min(rows_blk, m - r0);
+        e = cudaMemcpy2DAsync(stage, n * sizeof(T), X + r0 * ld, ld * sizeof(T), n * sizeof(T), rows,
+                              cudaMemcpyHostToDevice, h->stream);
+        if (e != cudaSuccess) break;
+        to_tf32_rows_kernel<T><<<grid, 256, 0, h->stream>>>(stage, n, rows, n, h->X32 + r0 * h->ldx32, h->ldx32);
+        h->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(stage);
+    if (e != cudaSuccess) return fail(h, PRMF_ERR_CUDA, "TF32 upload of X failed: %s", cudaGetErrorString(e));
+    return PRMF_OK;
+}
+
 int finish_X(prmf_handle* h) {
     // transposed copy for pass 1, then ||X||^2 partial of this rank, all-reduced once
     const int blocks = h->sm_count * 4;
-    if (h->m > 0) {
+    if (h->m > 0 && h->x_tf32) {
+        dim3 tg((unsigned)((h->n + 31) / 32), (unsigned)((h->m + 31) / 32));
+        transpose_f32_kernel<<<tg, 256, 0, h->stream>>>(h->X32, h->ldx32, h->m, h->n, h->Xt32, h->ldxt32);
+        LAUNCH_CHECK("transpose_f32_kernel");
+        sumsq_f32_kernel<<<blocks, 256, 0, h->stream>>>(h->X32, h->ldx32, h->m, h->n, h->scal_part);
+        LAUNCH_CHECK("sumsq_f32_kernel");
+        sum_partials_kernel<<<1, 256, 0, h->stream>>>(h->scal_part, blocks, h->normX_sq);
+        LAUNCH_CHECK("sum_partials_kernel");
+    } else if (h->m > 0) {
         dim3 tg((unsigned)((h->n + 31) / 32), (unsigned)((h->m + 31) / 32));
         transpose_kernel<<<tg, 256, 0, h->stream>>>(h->X, h->ldx, h->m, h->n, h->Xt, h->ldxt);
         LAUNCH_CHECK("transpose_kernel");
@@ -628,7 +795,13 @@ int prmf_abi_version(void) { return 1; }
 const char* prmf_last_error(const prmf_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global, int64_t n, int k, void* stream) {
+    return prmf_create_ex(out, device, m_local, m_global, n, k, stream, PRMF_X_F64);
+}
+
+int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_global, int64_t n, int k, void* stream,
+                   int x_dtype) {
     prmf_handle* h = nullptr;
+    if (x_dtype != PRMF_X_F64 && x_dtype != PRMF_X_TF32) return fail(h, PRMF_ERR_ARG, "unknown x_dtype %d", x_dtype);
     if (!out) return fail(h, PRMF_ERR_ARG, "out is NULL");
     *out = nullptr;
     if (m_local < 0 || n <= 0 || k <= 0 || m_global < m_local)
@@ -741,6 +914,12 @@ int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global
         }
     }
 
+    h->x_tf32 = x_dtype == PRMF_X_TF32;
+    if (h->x_tf32) {
+        h->use_fused = false;
+        setup_tf32(h);
+    }
+
     int rc = 0;
     const int64_t nk = n * k;
     const int kk2 = k * k;
@@ -753,10 +932,10 @@ int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global
         total += 3 * pad((size_t)(m_local + pad_rows) * k, d);                                      // U, U2, Ub
         if (h->use_fused)
             total += pad((size_t)h->fp.groups * kFExSlots * h->fp.panels * kFRS * kFKP * 2, sizeof(unsigned long long));
-        total += pad((size_t)std::max(h->chunks1, h->tchunks1) * std::max<int64_t>(1, m_local) * k, d);   // Apart
+        total += pad((size_t)std::max({h->chunks1, h->tchunks1, h->tc_chunks1}) * std::max<int64_t>(1, m_local) * k, d);   // Apart
         total += 2 * pad((size_t)(n + pad_rows) * k, d) + pad((size_t)nk, d);                      // Vbuf[2], Vb
         total += 2 * pad(kk2, d) + pad((size_t)std::max(h->uu_grid, h->fp.groups) * kk2, d) + pad((size_t)h->vu_grid * kk2, d);
-        total += pad(h->vu_grid, d) + pad((size_t)std::max({h->chunks, h->tchunks, h->fp.groups}) * nk, d);   // VB_part, Bpart
+        total += pad(h->vu_grid, d) + pad((size_t)std::max({h->chunks, h->tchunks, h->fp.groups, h->tc_chunks2}) * nk, d);   // VB_part, Bpart
         total += pad((size_t)nk + kk2 + 2, d) + pad(1, d) + pad((size_t)h->sm_count * 8, d) + pad(2, d);
         total += pad(1, sizeof(int)) + pad(1, sizeof(unsigned int)) + pad(k, sizeof(int32_t)) + pad(nk, sizeof(int32_t));
         total += pad((size_t)h->obj_capacity * kObjStride, d);
@@ -766,21 +945,28 @@ int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global
     }
 #define ALLOC(ptr, count) if (!rc) rc = dalloc(h, &ptr, (size_t)(count))
 #define TAKE(ptr, T, count) if (!rc) { ptr = h->arena.take<T>((size_t)(count)); if (!ptr) rc = fail(h, PRMF_ERR_NOMEM, "arena exhausted"); }
-    ALLOC(h->X, (size_t)std::max<int64_t>(1, m_local) * h->ldx);
-    ALLOC(h->Xt, (size_t)n * h->ldxt);
+    if (h->x_tf32) {
+        ALLOC(h->X32, (size_t)std::max<int64_t>(1, m_local) * h->ldx32);
+        ALLOC(h->Xt32, (size_t)n * h->ldxt32);
+        ALLOC(h->Vt32, (size_t)h->Kp * h->ldx32);
+        ALLOC(h->Ut32, (size_t)h->Kp * h->ldxt32);
+    } else {
+        ALLOC(h->X, (size_t)std::max<int64_t>(1, m_local) * h->ldx);
+        ALLOC(h->Xt, (size_t)n * h->ldxt);
+    }
     TAKE(h->U, double, (m_local + pad_rows) * k);
     TAKE(h->Ub, double, (m_local + pad_rows) * k);
     TAKE(h->U2, double, (m_local + pad_rows) * k);
     if (h->use_fused) {
         TAKE(h->fEx, unsigned long long, (size_t)h->fp.groups * kFExSlots * h->fp.panels * kFRS * kFKP * 2);
     }
-    TAKE(h->Apart, double, (size_t)std::max(h->chunks1, h->tchunks1) * std::max<int64_t>(1, m_local) * k);
+    TAKE(h->Apart, double, (size_t)std::max({h->chunks1, h->tchunks1, h->tc_chunks1}) * std::max<int64_t>(1, m_local) * k);
     TAKE(h->Vbuf[0], double, (n + pad_rows) * k); TAKE(h->Vbuf[1], double, (n + pad_rows) * k); TAKE(h->Vb, double, nk);
     TAKE(h->Gv, double, kk2); TAKE(h->Gvb, double, kk2);
     TAKE(h->Gu_part, double, (size_t)std::max(h->uu_grid, h->fp.groups) * kk2);
     TAKE(h->Gv_part, double, (size_t)h->vu_grid * kk2);
     TAKE(h->VB_part, double, h->vu_grid);
-    TAKE(h->Bpart, double, (size_t)std::max({h->chunks, h->tchunks, h->fp.groups}) * nk);
+    TAKE(h->Bpart, double, (size_t)std::max({h->chunks, h->tchunks, h->fp.groups, h->tc_chunks2}) * nk);
     TAKE(h->red, double, (size_t)nk + kk2 + 2);
     TAKE(h->normX_sq, double, 1);
     TAKE(h->scal_part, double, (size_t)h->sm_count * 8);
@@ -792,8 +978,14 @@ int prmf_create(prmf_handle** out, int device, int64_t m_local, int64_t m_global
     TAKE(h->obj, double, (size_t)h->obj_capacity * kObjStride);
 #undef TAKE
 #undef ALLOC
+    if (!rc && h->x_tf32) {
+        cudaMemsetAsync(h->Xt32, 0, sizeof(float) * n * h->ldxt32, h->stream);
+        cudaMemsetAsync(h->Vt32, 0, sizeof(float) * h->Kp * h->ldx32, h->stream);
+        cudaMemsetAsync(h->Ut32, 0, sizeof(float) * h->Kp * h->ldxt32, h->stream);
+        rc = finish_setup_tf32(h);
+    }
     if (!rc) {
-        cudaMemsetAsync(h->Xt, 0, sizeof(double) * n * h->ldxt, h->stream);
+        if (h->Xt) cudaMemsetAsync(h->Xt, 0, sizeof(double) * n * h->ldxt, h->stream);
         cudaMemsetAsync(h->ticket, 0, sizeof(unsigned int), h->stream);
         cudaMemsetAsync(h->U, 0, sizeof(double) * (m_local + pad_rows) * k, h->stream);
         cudaMemsetAsync(h->U2, 0, sizeof(double) * (m_local + pad_rows) * k, h->stream);
@@ -840,6 +1032,10 @@ int prmf_destroy(prmf_handle* h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->X) cudaFree(h->X);
     if (h->Xt) cudaFree(h->Xt);
+    if (h->X32) cudaFree(h->X32);
+    if (h->Xt32) cudaFree(h->Xt32);
+    if (h->Vt32) cudaFree(h->Vt32);
+    if (h->Ut32) cudaFree(h->Ut32);
     h->arena.release();
     h->pw_arena.release();
     h->as_arena.release();
@@ -852,6 +1048,10 @@ int prmf_set_X(prmf_handle* h, const double* X_host, int64_t ld) {
     if (!h) return PRMF_ERR_ARG;
     if ((!X_host && h->m > 0) || ld < h->n) return fail(h, PRMF_ERR_ARG, "prmf_set_X: bad pointer or ld < n");
     CU(cudaSetDevice(h->device));
+    if (h->x_tf32) {
+        int rc = store_tf32<double>(h, X_host, ld, true);
+        return rc ? rc : finish_X(h);
+    }
     if (h->m > 0) {
         CU(cudaMemsetAsync(h->X, 0, sizeof(double) * h->m * h->ldx, h->stream));
         CU(cudaMemcpy2DAsync(h->X, h->ldx * sizeof(double), X_host, ld * sizeof(double), h->n * sizeof(double),
@@ -864,6 +1064,10 @@ int prmf_set_X_device(prmf_handle* h, const double* X_dev, int64_t ld) {
     if (!h) return PRMF_ERR_ARG;
     if ((!X_dev && h->m > 0) || ld < h->n) return fail(h, PRMF_ERR_ARG, "prmf_set_X_device: bad pointer or ld < n");
     CU(cudaSetDevice(h->device));
+    if (h->x_tf32) {
+        int rc = store_tf32<double>(h, X_dev, ld, false);
+        return rc ? rc : finish_X(h);
+    }
     if (h->m > 0) {
         CU(cudaMemsetAsync(h->X, 0, sizeof(double) * h->m * h->ldx, h->stream));
         CU(cudaMemcpy2DAsync(h->X, h->ldx * sizeof(double), X_dev, ld * sizeof(double), h->n * sizeof(double),
@@ -871,6 +1075,17 @@ int prmf_set_X_device(prmf_handle* h, const double* X_dev, int64_t ld) {
     }
     return finish_X(h);
 }
+
+int prmf_set_X_f32(prmf_handle* h, const float* X, int64_t ld, int on_device) {
+    if (!h) return PRMF_ERR_ARG;
+    if (!h->x_tf32) return fail(h, PRMF_ERR_STATE, "prmf_set_X_f32 needs a handle created with PRMF_X_TF32");
+    if ((!X && h->m > 0) || ld < h->n) return fail(h, PRMF_ERR_ARG, "prmf_set_X_f32: bad pointer or ld < n");
+    CU(cudaSetDevice(h->device));
+    int rc = store_tf32<float>(h, X, ld, on_device == 0);
+    return rc ? rc : finish_X(h);
+}
+
+int prmf_x_dtype(const prmf_handle* h) { return h && h->x_tf32 ? PRMF_X_TF32 : PRMF_X_F64; }
 
 int prmf_get_normX_sq(prmf_handle* h, double* out) {
     if (!h || !out) return PRMF_ERR_ARG;
@@ -968,6 +1183,7 @@ int prmf_set_UV(prmf_handle* h, const double* U_local, const double* V) {
         CU(cudaMemcpyAsync(h->Vbuf[h->vcur], V, sizeof(double) * nk, cudaMemcpyHostToDevice, h->stream));
         int rc = recompute_Gv(h);
         if (rc) return rc;
+        if (h->x_tf32 && (rc = refresh_wt(h, h->Vbuf[h->vcur], h->n, h->Vt32, h->ldx32))) return rc;
     }
     CU(cudaStreamSynchronize(h->stream));
     if (V) h->have_UV = true;
@@ -1048,6 +1264,10 @@ int prmf_restore_best(prmf_handle* h) {
     const int64_t nk = h->n * h->k;
     CU(cudaMemcpyAsync(h->Vbuf[h->vcur], h->Vb, sizeof(double) * nk, cudaMemcpyDeviceToDevice, h->stream));
     CU(cudaMemcpyAsync(h->Gv, h->Gvb, sizeof(double) * h->k * h->k, cudaMemcpyDeviceToDevice, h->stream));
+    if (h->x_tf32) {
+        int rc = refresh_wt(h, h->Vbuf[h->vcur], h->n, h->Vt32, h->ldx32);
+        if (rc) return rc;
+    }
     CU(cudaStreamSynchronize(h->stream));
     return PRMF_OK;
 }
@@ -1061,7 +1281,11 @@ int prmf_residual_sq(prmf_handle* h, double* out) {
     int rc = dalloc(h, &d, 1);
     if (rc) return rc;
     if (h->m > 0) {
-        residual_kernel<<<blocks, 256, 0, h->stream>>>(h->X, h->ldx, h->m, (int)h->n, h->U, h->Vbuf[h->vcur], h->k, h->scal_part);
+        if (h->x_tf32)
+            residual_f32_kernel<<<blocks, 256, 0, h->stream>>>(h->X32, h->ldx32, h->m, (int)h->n, h->U, h->Vbuf[h->vcur], h->k,
+                                                                h->scal_part);
+        else
+            residual_kernel<<<blocks, 256, 0, h->stream>>>(h->X, h->ldx, h->m, (int)h->n, h->U, h->Vbuf[h->vcur], h->k, h->scal_part);
         h->launches++;
         sum_partials_kernel<<<1, 256, 0, h->stream>>>(h->scal_part, blocks, d);
         h->launches++;

@@ -25,13 +25,18 @@ def _ptr(a):
 class CudaEngine:
     """Owns the device-resident X row block, U, V, pathway tables and scratch of one rank."""
 
-    def __init__(self, m_local, m_global, n, k, device=0, stream=None):
+    def __init__(self, m_local, m_global, n, k, device=0, stream=None, x_dtype="f64"):
+        """x_dtype: "f64" (parity mode, X streamed in fp64) or "tf32" (opt-in: X stored as fp32 rounded to
+        tf32, X.V and X^T.U on the tcgen05 tensor cores; everything else stays fp64)."""
         self.lib = _lib.load()
         self.m, self.m_global, self.n, self.k = int(m_local), int(m_global), int(n), int(k)
         self.P = 0
+        if x_dtype not in _lib.X_DTYPES:
+            raise ValueError("x_dtype must be one of %s" % sorted(_lib.X_DTYPES))
+        self.x_dtype = x_dtype
         h = ctypes.c_void_p()
-        rc = self.lib.prmf_create(ctypes.byref(h), int(device), self.m, self.m_global, self.n, self.k,
-                                  ctypes.c_void_p(stream) if stream else None)
+        rc = self.lib.prmf_create_ex(ctypes.byref(h), int(device), self.m, self.m_global, self.n, self.k,
+                                     ctypes.c_void_p(stream) if stream else None, _lib.X_DTYPES[x_dtype])
         if rc != 0:
             msg = self.lib.prmf_last_error(None)
             raise _lib.PrmfLibraryError("prmf_create failed (%d): %s" % (rc, msg.decode() if msg else "?"))
@@ -64,16 +69,24 @@ class CudaEngine:
         """X: this rank's row block; a C-contiguous float64 numpy array (host) or a CUDA torch tensor."""
         if hasattr(X, "is_cuda") and X.is_cuda:
             import torch
-            if X.dtype != torch.float64 or X.dim() != 2 or X.stride(1) != 1:
-                raise ValueError("device X must be a 2-D float64 tensor with unit column stride")
+            f32_ok = self.x_dtype == "tf32" and X.dtype == torch.float32
+            if (X.dtype != torch.float64 and not f32_ok) or X.dim() != 2 or X.stride(1) != 1:
+                raise ValueError("device X must be a 2-D float64 tensor with unit column stride"
+                                 " (float32 is accepted by a tf32 engine)")
             if tuple(X.shape) != (self.m, self.n):
                 raise ValueError("X has shape %s, engine expects %s" % (tuple(X.shape), (self.m, self.n)))
             torch.cuda.current_stream(X.device).synchronize()
-            self._ck(self.lib.prmf_set_X_device(self.h, ctypes.c_void_p(X.data_ptr()), int(X.stride(0))))
+            if f32_ok:
+                self._ck(self.lib.prmf_set_X_f32(self.h, ctypes.c_void_p(X.data_ptr()), int(X.stride(0)), 1))
+            else:
+                self._ck(self.lib.prmf_set_X_device(self.h, ctypes.c_void_p(X.data_ptr()), int(X.stride(0))))
             return
         X = np.asarray(X)
         if X.shape != (self.m, self.n):
             raise ValueError("X has shape %s, engine expects %s" % (X.shape, (self.m, self.n)))
+        if self.x_dtype == "tf32" and X.dtype == np.float32 and X.strides[1] == 4 and X.strides[0] % 4 == 0:
+            self._ck(self.lib.prmf_set_X_f32(self.h, _ptr(X), X.strides[0] // 4 if self.m > 0 else self.n, 0))
+            return
         if X.dtype != np.float64 or X.strides[1] != 8 or X.strides[0] % 8 != 0:
             X = _f64(X)
         self._ck(self.lib.prmf_set_X(self.h, _ptr(X), X.strides[0] // 8 if self.m > 0 else self.n))

@@ -31,10 +31,10 @@ def _obj_dict(row):
             "fro": float(row[3]), "gamma": float(row[5]), "delta": float(row[6]), "obj": float(row[4])}
 
 
-def default_engine_factory(m_local, m_global, n, k, ctx):
+def default_engine_factory(m_local, m_global, n, k, ctx, x_dtype="f64"):
     """One CUDA engine per rank; with more than one rank the engines share an NCCL communicator."""
     device = ctx.local_rank if ctx.world > 1 else _current_device()
-    eng = CudaEngine(m_local, m_global, n, k, device=device)
+    eng = CudaEngine(m_local, m_global, n, k, device=device, x_dtype=x_dtype)
     return attach_collectives(eng, ctx)
 
 
@@ -268,13 +268,14 @@ def find_mins(V, pathways, nodelist=None):
 def nmf_pathway(X, Gs, gamma=1.0, delta=1.0, tradeoff=None, k_latent=6, tol=1e-3, max_iter=1000,
                 nodelist=None, modulus=10, U_init=None, V_init=None, verbose=False, *,
                 ctx=None, engine_factory=None, X_is_local=False, m_global=None, trace=None,
-                quiet=False):
+                quiet=False, x_dtype="f64"):
     """Pathway-regularised NMF, X ~ U V^T (prmf_runner.py:556-792), on one or more B200s.
 
     Positional / keyword arguments, return value, stdout lines, RNG consumption and error behaviour are
     the reference's.  Keyword-only extras: `ctx` (a `DistContext`; default: the initialised
     torch.distributed group, else single process), `X_is_local`/`m_global` (X is already this rank's row
-    block), `trace` (dict collecting per-iteration diagnostics), `quiet` (suppress the per-step prints).
+    block), `trace` (dict collecting per-iteration diagnostics), `quiet` (suppress the per-step prints),
+    `x_dtype` ("f64": parity mode; "tf32": opt-in tensor-core X streams, see include/prmf_b200.h).
     With several ranks every rank must call this with the same seed and arguments; all return the same
     full U, V and obj_data.
     """
@@ -300,7 +301,7 @@ def nmf_pathway(X, Gs, gamma=1.0, delta=1.0, tradeoff=None, k_latent=6, tol=1e-3
     if len(nodelist) != n:
         raise ValueError("nodelist has %d entries, X has %d columns" % (len(nodelist), n))
 
-    eng = factory(hi - lo, m, n, k_latent, ctx)
+    eng = factory(hi - lo, m, n, k_latent, ctx) if x_dtype == "f64" else factory(hi - lo, m, n, k_latent, ctx, x_dtype=x_dtype)
     try:
         eng.set_X(X_local)
         norm_X = math.sqrt(eng.normX_sq)                                    # :640

@@ -47,11 +47,14 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-inner-steps", type=int, default=2)
+    ap.add_argument("--x-dtype", default="f64", choices=["f64", "tf32"],
+                    help="f64: parity mode (default, the headline); tf32: opt-in tensor-core X streams (X stored fp32)")
     return ap.parse_args()
 
 
 def workload_name(a):
-    return "recount2-shape synthetic %dx%d fp64, k=%d, %d random KEGG-size pathways" % (a.m, a.n, a.k, a.pathways)
+    return "recount2-shape synthetic %dx%d %s, k=%d, %d random KEGG-size pathways" % (
+        a.m, a.n, "fp64" if a.x_dtype == "f64" else "fp32 (tf32 tensor-core X streams)", a.k, a.pathways)
 
 
 def make_pathways(a):
@@ -231,8 +234,11 @@ def run_ours(a):
 
     gen = torch.Generator(device="cuda")
     gen.manual_seed(1234 + ctx.rank)
-    Xd = torch.rand((m_local, a.n), dtype=torch.float64, device="cuda", generator=gen)
-    eng = CudaEngine(m_local, a.m, a.n, a.k, device=dev, stream=stream.cuda_stream)
+    tf32 = a.x_dtype == "tf32"
+    xdt = torch.float32 if tf32 else torch.float64
+    xsz = 4 if tf32 else 8
+    Xd = torch.rand((m_local, a.n), dtype=xdt, device="cuda", generator=gen)
+    eng = CudaEngine(m_local, a.m, a.n, a.k, device=dev, stream=stream.cuda_stream, x_dtype=a.x_dtype)
     attach_collectives(eng, ctx)
     eng.set_X(Xd)
     eng.set_pathways(packed)
@@ -312,20 +318,21 @@ def run_ours(a):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    bytes_xv = m_local * a.n * 8 + a.n * a.k * 8 + m_local * a.k * 8
-    bytes_xtu = m_local * a.n * 8 + m_local * a.k * 8 + a.n * a.k * 8
+    wsz = 4 if tf32 else 8                      # bytes per element of the W operand (fp32 transposed copy in tf32 mode)
+    bytes_xv = m_local * a.n * xsz + a.n * a.k * wsz + m_local * a.k * 8
+    bytes_xtu = m_local * a.n * xsz + m_local * a.k * wsz + a.n * a.k * 8
     phase_ms = {name: (tot / max(1, cnt)) for name, (tot, cnt) in kt.items()}
     xv_ms, xtu_ms = phase_ms["xv"], phase_ms["xtu"]
     ach_xv = bytes_xv / (xv_ms * 1e-3) / 1e9 if xv_ms > 0 else 0.0
     ach_xtu = bytes_xtu / (xtu_ms * 1e-3) / 1e9 if xtu_ms > 0 else 0.0
     step_bytes = bytes_xv + bytes_xtu
     inner_ms = ms_per_step / MODULUS
-    kname = "skinny_tma_kernel" if a.k <= 10 else "skinny_tma_gen_kernel"
+    kname = "tc_rowdot_kernel" if tf32 else "skinny_tma_kernel" if a.k <= 10 else "skinny_tma_gen_kernel"
     dominant = kname + (" pass 2 (X^T.U)" if xtu_ms >= xv_ms else " pass 1 (X.V)")
     ach = ach_xtu if xtu_ms >= xv_ms else ach_xv
     roofline = {
         "bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-        "traffic": NCU_TRAFFIC_CONFIG2 if (a.m, a.n, a.k, ctx.world) == (M, N_GENES, K, 1) else None,
+        "traffic": NCU_TRAFFIC_CONFIG2 if (a.m, a.n, a.k, ctx.world, tf32) == (M, N_GENES, K, 1, False) else None,
         "traffic_source": "profiles/r1_v2_skinny_tma_ncu_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
         "peak_source": peak_src,
         "xv": {"ms": xv_ms, "GBps": ach_xv, "frac": ach_xv / peak, "bytes": bytes_xv},
@@ -340,7 +347,7 @@ def run_ours(a):
     # e2e: the same outer iteration with HOST buffers (pinned X, U, V in; U, V, objective out)
     e2e = None
     if not a.no_e2e:
-        Xh = torch.empty((m_local, a.n), dtype=torch.float64, pin_memory=True)
+        Xh = torch.empty((m_local, a.n), dtype=xdt, pin_memory=True)
         Xh.copy_(Xd)
         del Xd
         Uh = torch.empty((m_local, a.k), dtype=torch.float64, pin_memory=True)
@@ -377,7 +384,7 @@ def run_ours(a):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
         e2e = {"value": 1000.0 / ems, "unit": UNIT, "ms_per_step": ems,
-               "h2d_bytes_per_step": int(m_local * a.n * 8 + (m_local + a.n) * a.k * 8),
+               "h2d_bytes_per_step": int(m_local * a.n * xsz + (m_local + a.n) * a.k * 8),
                "d2h_bytes_per_step": int((m_local + a.n) * a.k * 8 + MODULUS * 64 + 2 * a.k * packed.P * 8),
                "steps": n_e2e}
         Xcpu = Xn
@@ -390,7 +397,8 @@ def run_ours(a):
             np.random.seed(1)
             with contextlib.redirect_stderr(io.StringIO()):
                 t0 = time.perf_counter()
-                nmf_pathway(Xn, list(Gs), k_latent=a.k, nodelist=nodelist, max_iter=16 * MODULUS, quiet=True)
+                nmf_pathway(Xn, list(Gs), k_latent=a.k, nodelist=nodelist, max_iter=16 * MODULUS, quiet=True,
+                            x_dtype=a.x_dtype)
                 dt = time.perf_counter() - t0
             e2e["whole_solve"] = {"outer_iterations": 16, "seconds": dt, "value": 16 / dt, "unit": UNIT,
                                   "note": "nmf_pathway(X_host, graphs) -> (U, V) on the host, X uploaded once"}
@@ -399,7 +407,7 @@ def run_ours(a):
 
     cpu = None
     if ctx.rank == 0 and ctx.world == 1 and not a.no_cpu_baseline and Xcpu is not None:
-        rate, detail = cpu_outer_iteration_rate(np.asarray(Xcpu), Gs, nodelist, a.k, a.cpu_inner_steps)
+        rate, detail = cpu_outer_iteration_rate(np.asarray(Xcpu, dtype=np.float64), Gs, nodelist, a.k, a.cpu_inner_steps)
         cpu = {"value": rate, "unit": UNIT, "cores": host_threads(), "kind": "port",
                "sample": "%d inner steps + 1 restrict of the numpy/scipy oracle at full shape, extrapolated to 10 + 1"
                          % a.cpu_inner_steps, **detail}
@@ -410,13 +418,14 @@ def run_ours(a):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f64" if not tf32 else "tf32 X products (fp32 accumulate), f64 updates",
+            "data": "synthetic",
             "config": {"workload": workload_name(a), "step": "1 outer iteration = 10 inner steps + scores/restrict",
                        "parallelism": "rows of X,U sharded over %d GPU(s)" % a.gpus + (
                            "" if a.gpus == 1 else (", per-step all-reduce of [X^T U | U^T U]: " + (
                                "NCCL" if os.environ.get("PRMF_P2P", "1") == "0" else
                                "fused into the V-update kernel over NVLink peer memory"))),
-                       "l2": "inputs larger than L2 (X block %.2f GB per GPU per pass)" % (m_local * a.n * 8 / 1e9),
+                       "l2": "inputs larger than L2 (X block %.2f GB per GPU per pass)" % (m_local * a.n * xsz / 1e9),
                        "inner_steps_per_s": 1000.0 / inner_ms},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "final_obj": float(parts[-1, 4]),

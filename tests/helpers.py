@@ -60,3 +60,11 @@ def check_run_against_golden(g, U, V, od, trace, rtol_obj=1e-9, rtol_uv=1e-7):
     assert {k: [p for p, _ in v] for k, v in od["latent_to_pathway_data"].items()} == fm
     for key in ("recon", "manifold", "ignore", "fro", "gamma", "delta", "obj"):
         np.testing.assert_allclose(od[key], meta["final"][key], rtol=1e-8)
+
+
+def tf32_round(a):
+    """Host model of `cvt.rna.tf32.f32` applied to float(a): round to nearest (ties away from zero) to a
+    10-bit mantissa.  Returns float64 values that are exactly representable in tf32."""
+    b = np.asarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    b = ((b + 0x1000) & 0xFFFFE000).astype(np.uint32)
+    return b.view(np.float32).astype(np.float64)

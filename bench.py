@@ -259,8 +259,9 @@ def run_ours(a):
         eng.set_active(active)
         t1 = time.perf_counter()
         eng.step_async(MODULUS, gamma, delta)
-        mass, qn, _ = eng.scores()              # enqueued behind the 10 steps; one host wait
-        parts, _, _ = eng.step_collect(MODULUS)
+        # score tables enqueued behind the 10 steps, one host wait; the next block's X.V pass is already
+        # streaming while the host runs restrict and the multinomial draws (as prmf_b200.nmf_pathway does)
+        parts, _, _, (mass, qn, _) = eng.block_end(MODULUS, want_scores=True, prefetch=True)
         t2 = time.perf_counter()
         restrict_from_tables(mass, qn, full_cands)
         host_t[0] += (t1 - t0) + (time.perf_counter() - t2)
@@ -361,8 +362,7 @@ def run_ours(a):
             active = sample_active(full_cands, a.k)
             eng.set_active(active)
             eng.step_async(MODULUS, gamma, delta)
-            mass, qn, _ = eng.scores()
-            p, _, _ = eng.step_collect(MODULUS)
+            p, _, _, (mass, qn, _) = eng.block_end(MODULUS, want_scores=True, prefetch=False)
             restrict_from_tables(mass, qn, full_cands)
             Uo, Vo = eng.get_UV()               # D2H of the result
             return float(p[-1, 4]), Uo, Vo

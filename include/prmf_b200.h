@@ -117,6 +117,17 @@ int prmf_step_collect(prmf_handle* h, int n_steps, double* obj_parts, double* ga
  *   quad_raw[k][p]  = v_k^T L_p v_k                       (force_distinct_lapls :232; find_mins :49) */
 int prmf_scores(prmf_handle* h, double* mass, double* quad_norm, double* quad_raw);
 
+/* End of a block of inner steps in one call (nmf_pathway :739-768): the score tables of the current V (when
+ * want_scores != 0; same three tables as prmf_scores, any may be NULL), the objective rows of the last `n_steps`
+ * steps enqueued by prmf_step_async and gamma/delta, with ONE host wait.  With prefetch != 0 the library enqueues,
+ * before the host waits, the part of the NEXT inner step that does not depend on the active pathways (the X.V
+ * pass and the U update, :420-422): the GPU keeps streaming X while the host runs restrict / the multinomial
+ * draws.  The next prmf_step / prmf_step_async continues from there; prmf_get_UV, prmf_snapshot_best and the
+ * objective calls still see the U of the finished block; prmf_set_UV, prmf_restore_best and prmf_set_X discard
+ * the speculative work.  Results are identical with and without prefetch. */
+int prmf_block_end(prmf_handle* h, int n_steps, double* obj_parts, double* gamma_delta_out, int want_scores,
+                   double* mass, double* quad_norm, double* quad_raw, int prefetch);
+
 /* Best-iterate bookkeeping of nmf_pathway (:745-750, :778-782) without host traffic. */
 int prmf_snapshot_best(prmf_handle* h);
 int prmf_restore_best(prmf_handle* h);

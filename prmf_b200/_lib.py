@@ -34,6 +34,7 @@ SYMBOLS = {
     "prmf_step_async": (c_int, [_P, c_int, c_double, c_double, c_double]),
     "prmf_step_collect": (c_int, [_P, c_int, _P, _P]),
     "prmf_scores": (c_int, [_P, _P, _P, _P]),
+    "prmf_block_end": (c_int, [_P, c_int, _P, _P, c_int, _P, _P, _P, c_int]),
     "prmf_snapshot_best": (c_int, [_P]),
     "prmf_restore_best": (c_int, [_P]),
     "prmf_residual_sq": (c_int, [_P, POINTER(c_double)]),

@@ -276,6 +276,37 @@ u_update_kernel(double* __restrict__ U, const double* __restrict__ Apart, int ac
 }
 
 // ----------------------------------------------------------------------------------------------------
+// Packed pathway tables (device view)
+// ----------------------------------------------------------------------------------------------------
+struct Pathways {
+    int P;
+    const int64_t* path_ptr;     // P+1
+    const int32_t* support_idx;  // S
+    const int64_t* row_ptr;      // S+1
+    const int32_t* col_local;    // E
+    const double* w;             // E
+    const double* deg;           // S   column sums of W                         (:680)
+    const double* ldiag;         // S   diag(L) = deg - self-loop weight          (:683)
+    const double* isd;           // S   diag(L)^-1/2, 0 where diag(L) == 0        (:58-62)
+};
+
+// Normalised Laplacians of the k ACTIVE pathways, flattened for the objective (:344-352): one diagonal
+// entry per support row and one off-diagonal entry per stored edge, with global gene indices, so the
+// objective needs a single gather of V per entry instead of walking the packed CSR.
+struct ActiveSet {
+    int64_t n_diag, n_off;
+    const int32_t* diag_gene;    // gene of the support row
+    const int32_t* diag_factor;
+    const double* diag_coef;     // isd_r * diag(L)_r * isd_r
+    const int32_t* off_r;        // gene of the row
+    const int32_t* off_c;        // gene of the neighbour
+    const int32_t* off_lr;       // index of the row's diagonal entry (0..n_diag)
+    const int32_t* off_lc;       // index of the neighbour's diagonal entry
+    const int32_t* off_factor;
+    const double* off_coef;      // isd_r * (-w_rc * isd_c)   (0 for a self loop: it is part of diag(L))
+};
+
+// ----------------------------------------------------------------------------------------------------
 // The X-stream kernel, used for BOTH passes:   Out[chunk][j][k0:k0+KT] = sum_{i in chunk} M[i][j] * W[i][k0:k0+KT]
 //   pass 1  (U_up_num = X.V, :420):        M = Xt (genes x samples, the transposed copy), W = V -> A partials
 //   pass 2  (V_up_num_recon = X^T.U, :424): M = X  (samples x genes),                     W = U -> B partials
@@ -376,11 +407,290 @@ skinny_tn_kernel(const double* __restrict__ M, int64_t ldm, int64_t rows_total, 
 constexpr int kTmaConsumerWarps = 8;
 constexpr int kTmaThreads = (kTmaConsumerWarps + 1) * 32;
 
-template <int KT, int RS>
+// ----------------------------------------------------------------------------------------------------
+// Fused tails of the X-stream kernel (k <= 10).  The CTAs of one column panel cover different row chunks; once
+// all of them have stored their partials (a counter per panel, monotone over launches, so it never needs a
+// reset) the panel's rows are complete, and the SAME CTAs split them up and update them on the spot instead of
+// leaving that to a separate latency-bound launch:
+//   EPI 1 (pass 1, panel = samples): A = fixed-order sum of the chunk partials, U update (:421-422) into the
+//          second U buffer, partials of U_new^T U_new
+//   EPI 2 (pass 2, panel = genes, one GPU): B = fixed-order sum of the chunk partials, V update (:425-444) into
+//          the second V buffer, partials of V_new^T V_new and sum(V_new * B) for the objective
+//   EPI 3 (pass 2, sharded): B sums and the Gu sum written to the packed buffer that crosses NVLink
+// The per-CTA Gram partials are folded per panel by the last CTA of the panel to finish (second counter), so
+// the next consumer adds only `panels` terms.  All CTAs of the grid must be co-resident (they wait for each
+// other): the grid never exceeds the SM count and the launch is cooperative.  Only the 8 consumer warps take
+// part (the producer warp has exited): barriers are the named barrier 1.
+// ----------------------------------------------------------------------------------------------------
+struct EpiParams {
+    unsigned long long* arrive;   // per panel: CTAs whose partials are stored (monotone)
+    unsigned long long* done;     // per panel: CTAs whose share of the update is finished (monotone)
+    unsigned long long seq;       // 1-based launch number of this pass on this handle
+    double* part2;                // scratch: per-CTA Gram partials [panels*chunks][k*k]
+    double* vb2;                  // scratch: per-CTA sum(V_new * B) [panels*chunks]
+    // EPI 1
+    const double* Uold;
+    double* Unew;
+    const double* Gv;             // V^T V of the current V (k*k)
+    double* Gu_part;              // out: [panels][k*k]
+    // EPI 2
+    const double* Vold;
+    double* Vnew;
+    const double* Gu_part_in;     // [gu_parts][k*k]
+    int gu_parts;
+    Pathways pw;
+    const int32_t* active;
+    const int32_t* pos;
+    const double* gd;             // gamma, delta on the device
+    double* Gv_part;              // out: [panels][k*k]
+    double* VB_part;              // out: [panels]
+    // EPI 3
+    double* red;                  // [n*k | k*k | 2]
+};
+
+__device__ __forceinline__ void cons_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// fixed-order sum of `count` partials read from L2 (they were just written by other SMs)
+__device__ __forceinline__ double sum_strided_cg(const double* __restrict__ part, int count, int64_t stride) {
+    double s = 0.0;
+    int c = 0;
+    for (; c + 8 <= count; c += 8) {
+        double t[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t[q] = __ldcg(part + (int64_t)(c + q) * stride);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s += t[q];
+    }
+    for (; c < count; ++c) s += __ldcg(part + (int64_t)c * stride);
+    return s;
+}
+
+// wait until every CTA of this panel has stored its partials
+__device__ __forceinline__ void epi_panel_barrier(const EpiParams& ep, int panel) {
+    __threadfence();
+    cons_bar();
+    if (threadIdx.x == 0) {
+        atomicAdd(ep.arrive + panel, 1ull);
+        const unsigned long long target = ep.seq * gridDim.y;
+        while (ld_acquire_gpu_u64(ep.arrive + panel) < target) { }
+    }
+    cons_bar();
+}
+
+// this CTA's share of the update is stored; true in every thread of the panel's last CTA to get here
+__device__ __forceinline__ bool epi_panel_done(const EpiParams& ep, int panel, int* s_flag) {
+    __threadfence();
+    cons_bar();
+    if (threadIdx.x == 0) {
+        const unsigned long long prev = atomicAdd(ep.done + panel, 1ull);
+        *s_flag = prev + 1ull == ep.seq * gridDim.y;
+    }
+    cons_bar();
+    const bool last = *s_flag != 0;
+    if (last) __threadfence();
+    return last;
+}
+
+// out = T^T T for the `rows` x K tile in shared memory (256 threads; row slices combined in a fixed order)
+template <int K>
+__device__ __forceinline__ void epi_gram(const double* __restrict__ sT, int rows, double* __restrict__ sBuf,
+                                         double* __restrict__ out) {
+    constexpr int NP = K * K;
+    constexpr int NS = (256 / NP) > 8 ? 8 : (256 / NP);          // K <= 10: at least 2 slices
+    const int t = threadIdx.x;
+    const int rps = (max(rows, 0) + NS - 1) / NS;
+    if (t < NP * NS) {
+        const int pair = t % NP, sl = t / NP;
+        const int a = pair / K, b = pair - a * K;
+        const int rb = sl * rps, re = min(rows, rb + rps);
+        double g = 0.0;
+        for (int r = rb; r < re; ++r) g = fma(sT[r * K + a], sT[r * K + b], g);
+        sBuf[sl * NP + pair] = g;
+    }
+    cons_bar();
+    if (t < NP) {
+        double g = 0.0;
+#pragma unroll
+        for (int sl = 0; sl < NS; ++sl) g += sBuf[sl * NP + t];
+        out[t] = g;
+    }
+}
+
+// dst[e] = sum over `count` partials of src[c*stride + e] for e < n_el (contiguous elements; fixed order per
+// element), 4 elements x 4 partials of a thread in flight at a time instead of one dependent chain per element.
+__device__ __forceinline__ void epi_stage_sums(double* __restrict__ dst, const double* __restrict__ src, int n_el,
+                                               int count, int64_t stride) {
+    for (int e0 = threadIdx.x; e0 < n_el; e0 += 256 * 4) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        int c = 0;
+        for (; c + 4 <= count; c += 4) {
+            double v[4][4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    v[q][i] = (e0 + 256 * q < n_el) ? __ldcg(src + (int64_t)(c + i) * stride + e0 + 256 * q) : 0.0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[q] += v[q][i];
+        }
+        for (; c < count; ++c) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (e0 + 256 * q < n_el) acc[q] += __ldcg(src + (int64_t)c * stride + e0 + 256 * q);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (e0 + 256 * q < n_el) dst[e0 + 256 * q] = acc[q];
+    }
+}
+
+// rows [rb, rb + rows) of the panel belong to this CTA
+__device__ __forceinline__ void epi_share(int width, int64_t cols, int64_t c0, int& rb, int& rows) {
+    const int all = (int)max((int64_t)0, min((int64_t)width, cols - c0));
+    const int per = (all + (int)gridDim.y - 1) / (int)gridDim.y;
+    rb = (int)blockIdx.y * per;
+    rows = max(0, min(all, rb + per) - rb);
+}
+
+template <int K>
+__device__ __forceinline__ void epi_u_update(const EpiParams& ep, unsigned char* smem, int* s_flag, int panel, int64_t c0,
+                                             int width, int64_t cols, const double* __restrict__ Apart) {
+    const int t = threadIdx.x;
+    const int chunks = (int)gridDim.y;
+    int rb, rows;
+    epi_share(width, cols, c0, rb, rows);
+    const int n_el = rows * K;
+    double* sG = reinterpret_cast<double*>(smem);            // K*K (Gv), padded to 128 doubles
+    double* sBuf = sG + 128;                                 // 8 * K*K slice sums
+    double* sT = sBuf + 8 * K * K;                           // rows x K new rows
+    double* sA = sT + n_el;                                  // rows x K sums of the pass-1 partials
+    double* sU = sA + n_el;                                  // rows x K old rows
+    const int64_t base = (c0 + rb) * K;                      // this share is one contiguous run of rows
+    if (t < K * K) sG[t] = ep.Gv[t];
+    for (int e = t; e < n_el; e += 256) sU[e] = ep.Uold[base + e];
+    epi_panel_barrier(ep, panel);
+    epi_stage_sums(sA, Apart + base, n_el, chunks, cols * K);                               // X.V   (:420)
+    cons_bar();
+    for (int e = t; e < n_el; e += 256) {
+        const int r = e / K, c = e - r * K;
+        const double* urow = sU + r * K;
+        double den = 0.0;
+#pragma unroll
+        for (int l = 0; l < K; ++l) den = fma(urow[l], sG[l * K + c], den);
+        const double u = urow[c];
+        den += u;
+        const double f = (den != 0.0) ? sA[e] / den : 1.0;                                  // 0/0 := 1 (:422)
+        const double un = u * f;
+        sT[e] = un;
+        ep.Unew[base + e] = un;
+    }
+    cons_bar();
+    const int64_t me = (int64_t)panel * chunks + blockIdx.y;
+    epi_gram<K>(sT, rows, sBuf, ep.part2 + me * K * K);
+    if (!epi_panel_done(ep, panel, s_flag)) return;
+    if (t < K * K) ep.Gu_part[(int64_t)panel * K * K + t] = sum_strided_cg(ep.part2 + (int64_t)panel * chunks * K * K + t, chunks, K * K);
+}
+
+template <int K>
+__device__ __forceinline__ void epi_v_update(const EpiParams& ep, unsigned char* smem, int* s_flag, int panel, int64_t c0,
+                                             int width, int64_t cols, const double* __restrict__ Bpart) {
+    const int t = threadIdx.x;
+    const int chunks = (int)gridDim.y;
+    int rb, rows;
+    epi_share(width, cols, c0, rb, rows);
+    const int n_el = rows * K;
+    double* sG = reinterpret_cast<double*>(smem);            // K*K (Gu)
+    double* sBuf = sG + 128;
+    double* sT = sBuf + 8 * K * K;                           // rows x K new rows
+    double* sB = sT + n_el;                                  // rows x K sums of the pass-2 partials
+    double* sV = sB + n_el;                                  // rows x K old rows
+    double* sW = sG + 112;                                   // 8 warp sums (K*K <= 100 < 112)
+    const int64_t base = (c0 + rb) * K;
+    // Gu = sum over the sample panels of pass 1 (complete before this kernel started)
+    if (t < K * K) sG[t] = sum_strided(ep.Gu_part_in + t, ep.gu_parts, K * K);
+    for (int e = t; e < n_el; e += 256) sV[e] = ep.Vold[base + e];
+    const double gamma = ep.gd[0], delta = ep.gd[1];
+    epi_panel_barrier(ep, panel);
+    epi_stage_sums(sB, Bpart + base, n_el, chunks, cols * K);                               // X^T U  (:424)
+    cons_bar();
+    double vb = 0.0;
+    for (int e = t; e < n_el; e += 256) {
+        const int r = e / K, c = e - r * K;
+        const int64_t j = c0 + rb + r;
+        const double* vrow = sV + r * K;
+        const double b = sB[e];
+        double cden = 0.0;
+#pragma unroll
+        for (int l = 0; l < K; ++l) cden = fma(vrow[l], sG[l * K + c], cden);               // V.Gu   (:425)
+        const double v = vrow[c];
+        double num = b, den = cden;
+        const int32_t pr = ep.pos[j * K + c];
+        if (pr >= 0) {
+            const Pathways& pw = ep.pw;
+            const int64_t base = pw.path_ptr[ep.active[c]];
+            double wv = 0.0;
+            for (int64_t e2 = pw.row_ptr[pr]; e2 < pw.row_ptr[pr + 1]; ++e2)
+                wv = fma(pw.w[e2], ep.Vold[(int64_t)pw.support_idx[base + pw.col_local[e2]] * K + c], wv);
+            const double vp1 = v + 1.0;
+            const double man = gamma * wv;                                                  // :434
+            const double ign = delta * (1.0 / (vp1 * vp1));                                 // :438
+            num = b + (man + ign);                                                          // :440
+            den = cden + gamma * (pw.deg[pr] * v);                                          // :435,:441
+        }
+        if (den < kEps) den = kEps;                                                         // :442
+        double vn = v * (num / den);                                                        // :443
+        if (vn < kEps) vn = kEps;                                                           // :444
+        sT[e] = vn;
+        ep.Vnew[j * K + c] = vn;
+        vb = fma(vn, b, vb);
+    }
+    // sum(V_new * B) of this share: warp sums, then the 8 warp sums in order
+    vb = warp_sum(vb);
+    if ((t & 31) == 0) sW[t >> 5] = vb;
+    cons_bar();
+    const int64_t me = (int64_t)panel * chunks + blockIdx.y;
+    if (t == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += sW[w];
+        ep.vb2[me] = s;
+    }
+    epi_gram<K>(sT, rows, sBuf, ep.part2 + me * K * K);
+    if (!epi_panel_done(ep, panel, s_flag)) return;
+    if (t < K * K) ep.Gv_part[(int64_t)panel * K * K + t] = sum_strided_cg(ep.part2 + (int64_t)panel * chunks * K * K + t, chunks, K * K);
+    if (t == 128) ep.VB_part[panel] = sum_strided_cg(ep.vb2 + (int64_t)panel * chunks, chunks, 1);
+}
+
+template <int K>
+__device__ __forceinline__ void epi_pack(const EpiParams& ep, int panel, int64_t c0, int width, int64_t cols,
+                                         const double* __restrict__ Bpart) {
+    const int t = threadIdx.x;
+    const int chunks = (int)gridDim.y;
+    int rb, rows;
+    epi_share(width, cols, c0, rb, rows);
+    epi_panel_barrier(ep, panel);
+    const int64_t base = (c0 + rb) * K;
+    for (int e = t; e < rows * K; e += 256) ep.red[base + e] = sum_strided_cg(Bpart + base + e, chunks, cols * K);
+    if (panel == 0 && blockIdx.y == 0) {
+        const int64_t nk = cols * K;
+        if (t < K * K) ep.red[nk + t] = sum_strided(ep.Gu_part_in + t, ep.gu_parts, K * K);
+        if (t < 2) ep.red[nk + K * K + t] = 0.0;
+    }
+}
+
+template <int KT, int RS, int EPI>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 skinny_tma_kernel(const double* __restrict__ M, int64_t ldm, int64_t rows_total, int64_t cols,
                   const double* __restrict__ W, int panel_w, int64_t rows_per_chunk, int stages,
-                  double* __restrict__ OutPart) {
+                  double* __restrict__ OutPart, const EpiParams ep) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int panel = blockIdx.x;
     const int64_t chunk = blockIdx.y;
@@ -491,6 +801,12 @@ skinny_tma_kernel(const double* __restrict__ M, int64_t ldm, int64_t rows_total,
 #pragma unroll
             for (int c = 0; c < KT; ++c) out[c] = acc[g][c];
         }
+    }
+    if constexpr (EPI != 0) {
+        __shared__ int s_last;
+        if constexpr (EPI == 1) epi_u_update<KT>(ep, smem_raw, &s_last, panel, c0, width, cols, OutPart);
+        if constexpr (EPI == 2) epi_v_update<KT>(ep, smem_raw, &s_last, panel, c0, width, cols, OutPart);
+        if constexpr (EPI == 3) epi_pack<KT>(ep, panel, c0, width, cols, OutPart);
     }
 }
 
@@ -645,37 +961,6 @@ reduce_pack_kernel(const double* __restrict__ Bpart, int chunks, int64_t nk, con
         red[idx] = 0.0;
     }
 }
-
-// ----------------------------------------------------------------------------------------------------
-// Packed pathway tables (device view)
-// ----------------------------------------------------------------------------------------------------
-struct Pathways {
-    int P;
-    const int64_t* path_ptr;     // P+1
-    const int32_t* support_idx;  // S
-    const int64_t* row_ptr;      // S+1
-    const int32_t* col_local;    // E
-    const double* w;             // E
-    const double* deg;           // S   column sums of W                         (:680)
-    const double* ldiag;         // S   diag(L) = deg - self-loop weight          (:683)
-    const double* isd;           // S   diag(L)^-1/2, 0 where diag(L) == 0        (:58-62)
-};
-
-// Normalised Laplacians of the k ACTIVE pathways, flattened for the objective (:344-352): one diagonal
-// entry per support row and one off-diagonal entry per stored edge, with global gene indices, so the
-// objective needs a single gather of V per entry instead of walking the packed CSR.
-struct ActiveSet {
-    int64_t n_diag, n_off;
-    const int32_t* diag_gene;    // gene of the support row
-    const int32_t* diag_factor;
-    const double* diag_coef;     // isd_r * diag(L)_r * isd_r
-    const int32_t* off_r;        // gene of the row
-    const int32_t* off_c;        // gene of the neighbour
-    const int32_t* off_lr;       // index of the row's diagonal entry (0..n_diag)
-    const int32_t* off_lc;       // index of the neighbour's diagonal entry
-    const int32_t* off_factor;
-    const double* off_coef;      // isd_r * (-w_rc * isd_c)   (0 for a self loop: it is part of diag(L))
-};
 
 // pos[j*k + c] = packed row of gene j in the active pathway of factor c (or -1, preset by a memset), and
 // the flattened ActiveSet.  grid = (blocks, k); doff/eoff = per-factor offsets into the flat arrays.
@@ -1044,6 +1329,25 @@ v_update_objective_kernel(const double* __restrict__ Vold, double* __restrict__ 
     objective_block(Vnew, k, sGu, k > 64 ? Gv : sGv, k > 64 ? sGv : sV, scratch, Gv_part, VB_part, (int)gridDim.x, normX_sq,
                     as, Gv, gd, tradeoff, obj_out, step_counter, obj_capacity, sVh, kVhCap);
     TAIL_STAMP(5, true);
+}
+
+// Objective of one inner step as its own one-block launch (fused-tail path: the V update ran inside the pass-2
+// kernel and left per-panel partials).
+__global__ void __launch_bounds__(kTailThreads)
+objective_kernel(const double* __restrict__ V, int k, const double* __restrict__ Gu_part, int gu_parts,
+                 const double* __restrict__ Gv_part, const double* __restrict__ VB_part, int vparts,
+                 const double* __restrict__ normX_sq, ActiveSet as, double* __restrict__ Gv, double* __restrict__ gd,
+                 double tradeoff, double* __restrict__ obj_out, int* __restrict__ step_counter, int obj_capacity) {
+    extern __shared__ double sm[];
+    const int kk2 = k * k;
+    double* sGu = sm;
+    double* sGv = sm + kk2;
+    double* sSl = sGv + kk2;            // 1024 doubles
+    double* sVh = sSl + 1024;           // kVhCap doubles
+    __shared__ double scratch[5 * 32 + 128];
+    sum_gram_partials(sGu, Gu_part, gu_parts, kk2, sSl);
+    objective_block(V, k, sGu, sGv, sSl, scratch, Gv_part, VB_part, vparts, normX_sq, as, Gv, gd, tradeoff, obj_out,
+                    step_counter, obj_capacity, sVh, kVhCap);
 }
 
 // Gram of V from scratch (after prmf_set_UV): same tiling as the update kernel so partial layout matches.

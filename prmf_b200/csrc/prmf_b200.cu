@@ -114,6 +114,13 @@ struct prmf_handle {
     int64_t trows_per_chunk1 = 0, trows_per_chunk = 0;
     size_t tma_smem1 = 0, tma_smem2 = 0;
 
+    // fused tails (k <= 10, TMA path): the U / V updates run in the last CTA of each panel of the X-stream kernels
+    bool use_epi = false;
+    unsigned long long* epi_counters = nullptr;   // arrive | done, each [tpanels1 + tpanels], monotone over launches
+    unsigned long long epi_seq1 = 0, epi_seq2 = 0;
+    bool epi_coop = true;                     // cooperative launch (co-residency guaranteed by the driver)
+    double *epi_part2 = nullptr, *epi_vb2 = nullptr;
+
     // single-pass fused X kernel (opt-in: PRMF_FUSED=1)
     bool use_fused = false;
     FusedParams fp{};
@@ -143,6 +150,13 @@ struct prmf_handle {
     void* peer_base[kMaxPeers] = {nullptr};
     unsigned long long p2p_seq = 0;
     int p2p_parity = 0;
+
+    // Speculative pass 1: the first X.V pass (+ U update on the fused-tail path) of the NEXT inner step does not
+    // depend on the active pathways, so prmf_block_end enqueues it before the host waits for the score tables;
+    // the GPU streams X while the host runs restrict / sampling.  0: nothing ahead; 1: A partials ready, U
+    // untouched; 2: fused-tail path, h->U already holds U_new and h->U2 the current U.
+    int ahead = 0;
+    cudaEvent_t ev_sync = nullptr;
 
     // introspection
     int64_t launches = 0;
@@ -241,15 +255,42 @@ template <int KT>
 int launch_skinny_tma_t(prmf_handle* h, const double* M, int64_t ldm, int64_t rows, int64_t cols, const double* W,
                         int panels, int panel_w, int chunks, int64_t rows_per_chunk, size_t smem, double* out) {
     dim3 grid(panels, chunks);
+    const EpiParams none{};
     if (h->tma_rs == 4) {
-        CU(cudaFuncSetAttribute(skinny_tma_kernel<KT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        skinny_tma_kernel<KT, 4><<<grid, kTmaThreads, smem, h->stream>>>(M, ldm, rows, cols, W, panel_w, rows_per_chunk,
-                                                                         h->tma_stages, out);
+        CU(cudaFuncSetAttribute(skinny_tma_kernel<KT, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        skinny_tma_kernel<KT, 4, 0><<<grid, kTmaThreads, smem, h->stream>>>(M, ldm, rows, cols, W, panel_w, rows_per_chunk,
+                                                                            h->tma_stages, out, none);
     } else {
-        CU(cudaFuncSetAttribute(skinny_tma_kernel<KT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        skinny_tma_kernel<KT, 8><<<grid, kTmaThreads, smem, h->stream>>>(M, ldm, rows, cols, W, panel_w, rows_per_chunk,
-                                                                         h->tma_stages, out);
+        CU(cudaFuncSetAttribute(skinny_tma_kernel<KT, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        skinny_tma_kernel<KT, 8, 0><<<grid, kTmaThreads, smem, h->stream>>>(M, ldm, rows, cols, W, panel_w, rows_per_chunk,
+                                                                            h->tma_stages, out, none);
     }
+    return PRMF_OK;
+}
+
+// X-stream kernel with a fused tail (EPI 1: U update, 2: V update, 3: pack for the exchange over ranks).  The CTAs
+// of a panel wait for each other, so the launch is cooperative (all CTAs co-resident or the launch fails).
+template <int KT>
+int launch_skinny_epi_t(prmf_handle* h, int epi, const double* M, int64_t ldm, int64_t rows, int64_t cols,
+                        const double* W, int panels, int panel_w, int chunks, int64_t rows_per_chunk, size_t smem,
+                        double* out, const EpiParams& ep_in) {
+    dim3 grid(panels, chunks);
+    EpiParams ep = ep_in;
+    int stages = h->tma_stages;
+    void* args[] = {(void*)&M, (void*)&ldm, (void*)&rows, (void*)&cols, (void*)&W, (void*)&panel_w,
+                    (void*)&rows_per_chunk, (void*)&stages, (void*)&out, (void*)&ep};
+    const void* fn = nullptr;
+    switch (epi) {
+        case 1: fn = (const void*)skinny_tma_kernel<KT, 8, 1>; break;
+        case 2: fn = (const void*)skinny_tma_kernel<KT, 8, 2>; break;
+        case 3: fn = (const void*)skinny_tma_kernel<KT, 8, 3>; break;
+        default: return fail(h, PRMF_ERR_STATE, "bad fused-tail id %d", epi);
+    }
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (h->epi_coop)
+        CU(cudaLaunchCooperativeKernel(fn, grid, dim3(kTmaThreads), args, smem, h->stream));
+    else
+        CU(cudaLaunchKernel(fn, grid, dim3(kTmaThreads), args, smem, h->stream));
     return PRMF_OK;
 }
 
@@ -524,8 +565,9 @@ int ensure_pos(prmf_handle* h) {
     int32_t* of = olc + h->as_cap_off;
     double* dc = h->as_f64;
     double* oc = dc + h->as_cap_diag;
+    // (pageable source: the runtime stages the bytes before the call returns, so `offs` may go out of scope
+    //  and the host does not wait for work still queued on the stream, e.g. a speculative pass 1)
     CU(cudaMemcpyAsync(h->as_off, offs.data(), sizeof(int64_t) * offs.size(), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaStreamSynchronize(h->stream));      // offs is a stack-local host buffer
     CU(cudaMemsetAsync(h->pos, 0xff, sizeof(int32_t) * h->n * h->k, h->stream));
     dim3 grid(4, h->k);
     build_active_kernel<<<grid, 128, 0, h->stream>>>(h->pw, h->active, k, h->as_off, h->as_off + (k + 1), h->pos, dg, df,
@@ -535,6 +577,90 @@ int ensure_pos(prmf_handle* h) {
     h->as.diag_gene = dg; h->as.diag_factor = df; h->as.diag_coef = dc;
     h->as.off_r = orr; h->as.off_c = occ; h->as.off_lr = olr; h->as.off_lc = olc; h->as.off_factor = of; h->as.off_coef = oc;
     h->pos_dirty = false;
+    return PRMF_OK;
+}
+
+// ---- fused-tail path (use_epi): two X-stream launches per inner step do the U and V updates as well ----
+int launch_xv_epi(prmf_handle* h) {
+    EpiParams ep{};
+    const size_t np = (size_t)h->tpanels1 + h->tpanels;
+    ep.arrive = h->epi_counters;
+    ep.done = h->epi_counters + np;
+    ep.seq = ++h->epi_seq1;
+    ep.part2 = h->epi_part2;
+    ep.vb2 = h->epi_vb2;
+    ep.Uold = h->U;
+    ep.Unew = h->U2;
+    ep.Gv = h->Gv;
+    ep.Gu_part = h->Gu_part;
+    int rc = 0;
+    KT_SWITCH_RC(h->k, rc, launch_skinny_epi_t, h, 1, h->Xt, h->ldxt, h->n, h->m, h->Vbuf[h->vcur], h->tpanels1,
+                 h->tpanel_w1, h->tchunks1, h->trows_per_chunk1, h->tma_smem1, h->Apart, ep);
+    if (rc) return rc;
+    LAUNCH_CHECK("skinny_tma_kernel(pass 1 + U update)");
+    std::swap(h->U, h->U2);
+    return PRMF_OK;
+}
+
+int launch_xtu_epi(prmf_handle* h, double* packed_dst) {
+    EpiParams ep{};
+    const size_t np = (size_t)h->tpanels1 + h->tpanels;
+    ep.arrive = h->epi_counters + h->tpanels1;
+    ep.done = h->epi_counters + np + h->tpanels1;
+    ep.seq = ++h->epi_seq2;
+    ep.part2 = h->epi_part2;
+    ep.vb2 = h->epi_vb2;
+    ep.Gu_part_in = h->Gu_part;
+    ep.gu_parts = h->tpanels1;
+    const bool pack = packed_dst != nullptr;
+    if (pack) {
+        ep.red = packed_dst;
+    } else {
+        ep.Vold = h->Vbuf[h->vcur];
+        ep.Vnew = h->Vbuf[h->vcur ^ 1];
+        ep.pw = h->pw;
+        ep.active = h->active;
+        ep.pos = h->pos;
+        ep.gd = h->gd;
+        ep.Gv_part = h->Gv_part;
+        ep.VB_part = h->VB_part;
+    }
+    int rc = 0;
+    KT_SWITCH_RC(h->k, rc, launch_skinny_epi_t, h, pack ? 3 : 2, h->X, h->ldx, h->m, h->n, h->U, h->tpanels, h->tpanel_w,
+                 h->tchunks, h->trows_per_chunk, h->tma_smem2, h->Bpart, ep);
+    if (rc) return rc;
+    LAUNCH_CHECK(pack ? "skinny_tma_kernel(pass 2 + pack)" : "skinny_tma_kernel(pass 2 + V update)");
+    if (!pack) h->vcur ^= 1;
+    return PRMF_OK;
+}
+
+int launch_objective(prmf_handle* h, double tradeoff) {
+    const size_t smem = sizeof(double) * (2 * (size_t)h->k * h->k + 1024 + kVhCap);
+    objective_kernel<<<1, kTailThreads, smem, h->stream>>>(h->Vbuf[h->vcur], h->k, h->Gu_part, h->tpanels1, h->Gv_part,
+                                                           h->VB_part, h->tpanels, h->normX_sq, h->as, h->Gv, h->gd,
+                                                           tradeoff, h->obj, h->step_counter, h->obj_capacity);
+    LAUNCH_CHECK("objective_kernel");
+    return PRMF_OK;
+}
+
+const double* cur_U(const prmf_handle* h) { return h->ahead == 2 ? h->U2 : h->U; }
+
+void cancel_ahead(prmf_handle* h) {
+    if (h->ahead == 2) std::swap(h->U, h->U2);
+    h->ahead = 0;
+}
+
+int prefetch_pass1(prmf_handle* h) {
+    if (h->ahead || h->profiling || h->use_fused || h->m == 0) return PRMF_OK;
+    if (!h->have_X || !h->have_UV) return PRMF_OK;
+    int rc = 0;
+    if (h->use_epi) {
+        if ((rc = launch_xv_epi(h))) return rc;
+        h->ahead = 2;
+    } else {
+        if ((rc = launch_xv(h))) return rc;
+        h->ahead = 1;
+    }
     return PRMF_OK;
 }
 
@@ -600,11 +726,34 @@ int enqueue_steps(prmf_handle* h, int n_steps, double gamma, double delta, doubl
         cudaEventRecord(h->ev_pool[h->ev_pairs.back().second + 1], h->stream);
     };
     for (int s = 0; s < n_steps; ++s) {
+        const bool skip_pass1 = s == 0 && h->ahead != 0;      // already enqueued by prmf_block_end
+        if (skip_pass1) h->ahead = 0;
+        if (h->use_epi) {
+            if (!skip_pass1) { tic(0); rc = launch_xv_epi(h); toc(); }
+            if (rc) return rc;
+            if (h->comm == nullptr) {
+                tic(2); rc = launch_xtu_epi(h, nullptr); toc();
+                if (rc) return rc;
+                tic(5); rc = launch_objective(h, tradeoff); toc();
+                if (rc) return rc;
+            } else {
+                double* dst = h->p2p_ready ? h->p2p_buf + (size_t)h->p2p_parity * h->p2p_red_count : h->red;
+                tic(2); rc = launch_xtu_epi(h, dst); toc();
+                if (rc) return rc;
+                if (!h->p2p_ready) {
+                    tic(3); rc = allreduce(h, h->red, red_count); toc();
+                    if (rc) return rc;
+                }
+                tic(4); rc = launch_v_update_objective(h, true, tradeoff); toc();
+                if (rc) return rc;
+            }
+            continue;
+        }
         if (h->use_fused) {
             tic(0); rc = launch_fused(h); toc();
             if (rc) return rc;
         } else {
-            tic(0); rc = launch_xv(h); toc();
+            if (!skip_pass1) { tic(0); rc = launch_xv(h); toc(); }
             if (rc) return rc;
             tic(1); rc = launch_u_update(h); toc();
             if (rc) return rc;
@@ -757,6 +906,7 @@ int store_tf32(prmf_handle* h, const T* X, int64_t ld, bool on_host) {
 }
 
 int finish_X(prmf_handle* h) {
+    cancel_ahead(h);
     // transposed copy for pass 1, then ||X||^2 partial of this rank, all-reduced once
     const int blocks = h->sm_count * 4;
     if (h->m > 0 && h->x_tf32) {
@@ -919,6 +1069,24 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
         h->use_fused = false;
         setup_tf32(h);
     }
+    {
+        const char* ee = getenv("PRMF_EPI");
+        h->use_epi = !(ee && atoi(ee) == 0) && h->use_tma && k <= 10 && h->tma_rs == 8 && m_local > 0 && !h->x_tf32 &&
+                     !h->use_fused && h->tpanels1 * h->tchunks1 <= h->sm_count && h->tpanels * h->tchunks <= h->sm_count;
+        const char* ec = getenv("PRMF_COOP");
+        h->epi_coop = !(ec && atoi(ec) == 0);
+        if (h->use_epi) {
+            // the last CTA of a panel reuses the ring for Gv/Gu, the slice sums and the panel's new rows
+            const size_t share1 = (size_t)(h->tpanel_w1 + h->tchunks1 - 1) / h->tchunks1 * k;
+            const size_t share2 = (size_t)(h->tpanel_w + h->tchunks - 1) / h->tchunks * k;
+            const size_t need1 = sizeof(double) * (128 + 8 * (size_t)k * k + 3 * share1);
+            const size_t need2 = sizeof(double) * (128 + 8 * (size_t)k * k + 3 * share2);
+            h->tma_smem1 = std::max(h->tma_smem1, need1);
+            h->tma_smem2 = std::max(h->tma_smem2, need2);
+        }
+    }
+    const int gu_parts_max = std::max({h->uu_grid, h->fp.groups, h->use_epi ? h->tpanels1 : 0});
+    const int gv_parts_max = std::max(h->vu_grid, h->use_epi ? h->tpanels : 0);
 
     int rc = 0;
     const int64_t nk = n * k;
@@ -934,8 +1102,11 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
             total += pad((size_t)h->fp.groups * kFExSlots * h->fp.panels * kFRS * kFKP * 2, sizeof(unsigned long long));
         total += pad((size_t)std::max({h->chunks1, h->tchunks1, h->tc_chunks1}) * std::max<int64_t>(1, m_local) * k, d);   // Apart
         total += 2 * pad((size_t)(n + pad_rows) * k, d) + pad((size_t)nk, d);                      // Vbuf[2], Vb
-        total += 2 * pad(kk2, d) + pad((size_t)std::max(h->uu_grid, h->fp.groups) * kk2, d) + pad((size_t)h->vu_grid * kk2, d);
-        total += pad(h->vu_grid, d) + pad((size_t)std::max({h->chunks, h->tchunks, h->fp.groups, h->tc_chunks2}) * nk, d);   // VB_part, Bpart
+        total += 2 * pad(kk2, d) + pad((size_t)gu_parts_max * kk2, d) + pad((size_t)gv_parts_max * kk2, d);
+        total += pad(gv_parts_max, d) + pad((size_t)std::max({h->chunks, h->tchunks, h->fp.groups, h->tc_chunks2}) * nk, d);   // VB_part, Bpart
+        total += pad(2 * ((size_t)h->tpanels1 + h->tpanels) + 2, sizeof(unsigned long long));     // fused-tail counters
+        total += pad((size_t)std::max(h->tpanels1 * h->tchunks1, h->tpanels * h->tchunks) * kk2, d) +
+                 pad((size_t)h->tpanels * h->tchunks, d);                                          // per-CTA partials
         total += pad((size_t)nk + kk2 + 2, d) + pad(1, d) + pad((size_t)h->sm_count * 8, d) + pad(2, d);
         total += pad(1, sizeof(int)) + pad(1, sizeof(unsigned int)) + pad(k, sizeof(int32_t)) + pad(nk, sizeof(int32_t));
         total += pad((size_t)h->obj_capacity * kObjStride, d);
@@ -963,9 +1134,12 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
     TAKE(h->Apart, double, (size_t)std::max({h->chunks1, h->tchunks1, h->tc_chunks1}) * std::max<int64_t>(1, m_local) * k);
     TAKE(h->Vbuf[0], double, (n + pad_rows) * k); TAKE(h->Vbuf[1], double, (n + pad_rows) * k); TAKE(h->Vb, double, nk);
     TAKE(h->Gv, double, kk2); TAKE(h->Gvb, double, kk2);
-    TAKE(h->Gu_part, double, (size_t)std::max(h->uu_grid, h->fp.groups) * kk2);
-    TAKE(h->Gv_part, double, (size_t)h->vu_grid * kk2);
-    TAKE(h->VB_part, double, h->vu_grid);
+    TAKE(h->Gu_part, double, (size_t)gu_parts_max * kk2);
+    TAKE(h->Gv_part, double, (size_t)gv_parts_max * kk2);
+    TAKE(h->VB_part, double, gv_parts_max);
+    TAKE(h->epi_counters, unsigned long long, 2 * ((size_t)h->tpanels1 + h->tpanels) + 2);
+    TAKE(h->epi_part2, double, (size_t)std::max(h->tpanels1 * h->tchunks1, h->tpanels * h->tchunks) * kk2);
+    TAKE(h->epi_vb2, double, (size_t)h->tpanels * h->tchunks);
     TAKE(h->Bpart, double, (size_t)std::max({h->chunks, h->tchunks, h->fp.groups, h->tc_chunks2}) * nk);
     TAKE(h->red, double, (size_t)nk + kk2 + 2);
     TAKE(h->normX_sq, double, 1);
@@ -987,6 +1161,7 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
     if (!rc) {
         if (h->Xt) cudaMemsetAsync(h->Xt, 0, sizeof(double) * n * h->ldxt, h->stream);
         cudaMemsetAsync(h->ticket, 0, sizeof(unsigned int), h->stream);
+        cudaMemsetAsync(h->epi_counters, 0, sizeof(unsigned long long) * (2 * ((size_t)h->tpanels1 + h->tpanels) + 2), h->stream);
         cudaMemsetAsync(h->U, 0, sizeof(double) * (m_local + pad_rows) * k, h->stream);
         cudaMemsetAsync(h->U2, 0, sizeof(double) * (m_local + pad_rows) * k, h->stream);
         if (h->use_fused) {
@@ -997,7 +1172,7 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
         cudaMemsetAsync(h->Vbuf[0], 0, sizeof(double) * (n + pad_rows) * k, h->stream);
         cudaMemsetAsync(h->Vbuf[1], 0, sizeof(double) * (n + pad_rows) * k, h->stream);
         cudaMemsetAsync(h->red, 0, sizeof(double) * (nk + kk2 + 2), h->stream);
-        cudaMemsetAsync(h->Gu_part, 0, sizeof(double) * std::max(h->uu_grid, h->fp.groups) * kk2, h->stream);
+        cudaMemsetAsync(h->Gu_part, 0, sizeof(double) * gu_parts_max * kk2, h->stream);
         e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) rc = fail(h, PRMF_ERR_CUDA, "init memset: %s", cudaGetErrorString(e));
     }
@@ -1028,6 +1203,7 @@ int prmf_destroy(prmf_handle* h) {
     if (h->p2p_ready)
         for (int r = 0; r < h->nranks; ++r)
             if (r != h->rank && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
+    if (h->ev_sync) cudaEventDestroy(h->ev_sync);
     if (h->p2p_buf) cudaFree(h->p2p_buf);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->X) cudaFree(h->X);
@@ -1176,6 +1352,7 @@ int prmf_set_pathways(prmf_handle* h, int32_t P, const int64_t* path_ptr, const 
 int prmf_set_UV(prmf_handle* h, const double* U_local, const double* V) {
     if (!h) return PRMF_ERR_ARG;
     CU(cudaSetDevice(h->device));
+    cancel_ahead(h);
     if (U_local && h->m > 0)
         CU(cudaMemcpyAsync(h->U, U_local, sizeof(double) * h->m * h->k, cudaMemcpyHostToDevice, h->stream));
     if (V) {
@@ -1194,7 +1371,7 @@ int prmf_get_UV(prmf_handle* h, double* U_local, double* V) {
     if (!h) return PRMF_ERR_ARG;
     CU(cudaSetDevice(h->device));
     if (U_local && h->m > 0)
-        CU(cudaMemcpyAsync(U_local, h->U, sizeof(double) * h->m * h->k, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(U_local, cur_U(h), sizeof(double) * h->m * h->k, cudaMemcpyDeviceToHost, h->stream));
     if (V) CU(cudaMemcpyAsync(V, h->Vbuf[h->vcur], sizeof(double) * h->n * h->k, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return PRMF_OK;
@@ -1248,10 +1425,44 @@ int prmf_scores(prmf_handle* h, double* mass, double* quad_norm, double* quad_ra
     return PRMF_OK;
 }
 
+int prmf_block_end(prmf_handle* h, int n_steps, double* obj_parts, double* gamma_delta_out, int want_scores,
+                   double* mass, double* quad_norm, double* quad_raw, int prefetch) {
+    if (!h) return PRMF_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    if (n_steps > h->obj_capacity) return fail(h, PRMF_ERR_ARG, "prmf_block_end: more steps than were run");
+    if (want_scores) {
+        if (!h->have_pw || !h->have_UV) return fail(h, PRMF_ERR_STATE, "prmf_block_end needs pathways and V for the scores");
+        const size_t cnt = (size_t)h->k * h->pw.P;
+        double* d = h->scores_buf;
+        scores_kernel<<<std::min(h->pw.P, h->sm_count * 8), 256, 0, h->stream>>>(h->Vbuf[h->vcur], h->k, h->Gv, h->pw, d,
+                                                                                 d + cnt, d + 2 * cnt);
+        LAUNCH_CHECK("scores_kernel");
+        if (mass) CU(cudaMemcpyAsync(mass, d, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (quad_norm) CU(cudaMemcpyAsync(quad_norm, d + cnt, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (quad_raw) CU(cudaMemcpyAsync(quad_raw, d + 2 * cnt, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (obj_parts && n_steps > 0)
+        CU(cudaMemcpyAsync(obj_parts, h->obj, sizeof(double) * n_steps * kObjStride, cudaMemcpyDeviceToHost, h->stream));
+    if (gamma_delta_out)
+        CU(cudaMemcpyAsync(gamma_delta_out, h->gd, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (!h->ev_sync) CU(cudaEventCreateWithFlags(&h->ev_sync, cudaEventDisableTiming));
+    CU(cudaEventRecord(h->ev_sync, h->stream));
+    if (prefetch) {
+        int rc = prefetch_pass1(h);              // streams X while the host digests the tables
+        if (rc) return rc;
+    }
+    CU(cudaEventSynchronize(h->ev_sync));
+    if (h->profiling) {
+        CU(cudaStreamSynchronize(h->stream));
+        harvest_events(h);
+    }
+    return PRMF_OK;
+}
+
 int prmf_snapshot_best(prmf_handle* h) {
     if (!h) return PRMF_ERR_ARG;
     CU(cudaSetDevice(h->device));
-    if (h->m > 0) CU(cudaMemcpyAsync(h->Ub, h->U, sizeof(double) * h->m * h->k, cudaMemcpyDeviceToDevice, h->stream));
+    if (h->m > 0) CU(cudaMemcpyAsync(h->Ub, cur_U(h), sizeof(double) * h->m * h->k, cudaMemcpyDeviceToDevice, h->stream));
     CU(cudaMemcpyAsync(h->Vb, h->Vbuf[h->vcur], sizeof(double) * h->n * h->k, cudaMemcpyDeviceToDevice, h->stream));
     CU(cudaMemcpyAsync(h->Gvb, h->Gv, sizeof(double) * h->k * h->k, cudaMemcpyDeviceToDevice, h->stream));
     return PRMF_OK;
@@ -1260,6 +1471,7 @@ int prmf_snapshot_best(prmf_handle* h) {
 int prmf_restore_best(prmf_handle* h) {
     if (!h) return PRMF_ERR_ARG;
     CU(cudaSetDevice(h->device));
+    cancel_ahead(h);
     if (h->m > 0) CU(cudaMemcpyAsync(h->U, h->Ub, sizeof(double) * h->m * h->k, cudaMemcpyDeviceToDevice, h->stream));
     const int64_t nk = h->n * h->k;
     CU(cudaMemcpyAsync(h->Vbuf[h->vcur], h->Vb, sizeof(double) * nk, cudaMemcpyDeviceToDevice, h->stream));
@@ -1282,10 +1494,10 @@ int prmf_residual_sq(prmf_handle* h, double* out) {
     if (rc) return rc;
     if (h->m > 0) {
         if (h->x_tf32)
-            residual_f32_kernel<<<blocks, 256, 0, h->stream>>>(h->X32, h->ldx32, h->m, (int)h->n, h->U, h->Vbuf[h->vcur], h->k,
+            residual_f32_kernel<<<blocks, 256, 0, h->stream>>>(h->X32, h->ldx32, h->m, (int)h->n, cur_U(h), h->Vbuf[h->vcur], h->k,
                                                                 h->scal_part);
         else
-            residual_kernel<<<blocks, 256, 0, h->stream>>>(h->X, h->ldx, h->m, (int)h->n, h->U, h->Vbuf[h->vcur], h->k, h->scal_part);
+            residual_kernel<<<blocks, 256, 0, h->stream>>>(h->X, h->ldx, h->m, (int)h->n, cur_U(h), h->Vbuf[h->vcur], h->k, h->scal_part);
         h->launches++;
         sum_partials_kernel<<<1, 256, 0, h->stream>>>(h->scal_part, blocks, d);
         h->launches++;
@@ -1316,7 +1528,7 @@ int prmf_objective(prmf_handle* h, double gamma, double delta, double* out) {
     const int blocks = h->sm_count * 4;
     const int64_t mk = h->m * h->k;
     if (mk > 0) {                                                              // sum(U^2) (:359); U is zero padded
-        sumsq_kernel<<<blocks, 256, 0, h->stream>>>(h->U, mk + 2, 1, (int)round_up(mk, 2), h->scal_part);
+        sumsq_kernel<<<blocks, 256, 0, h->stream>>>(cur_U(h), mk + 2, 1, (int)round_up(mk, 2), h->scal_part);
         h->launches++;
         sum_partials_kernel<<<1, 256, 0, h->stream>>>(h->scal_part, blocks, d + 2);
         h->launches++;

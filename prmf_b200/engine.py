@@ -154,6 +154,20 @@ class CudaEngine:
         self._ck(self.lib.prmf_scores(self.h, _ptr(mass), _ptr(qn), _ptr(qr)))
         return mass, qn, qr
 
+    def block_end(self, n_steps, want_scores=True, prefetch=True):
+        """Collect a block enqueued by `step_async` with one host wait: (parts[n_steps, 8], gamma_next,
+        delta_next, tables) where tables is (mass, quad_norm, quad_raw) or None.  `prefetch` lets the GPU start
+        the next inner step's X.V pass while the host works on the tables (see prmf_block_end)."""
+        parts = np.empty((n_steps, _lib.OBJ_STRIDE))
+        gd = np.empty(2)
+        tables = None
+        if want_scores:
+            tables = tuple(np.empty((self.k, self.P)) for _ in range(3))
+        self._ck(self.lib.prmf_block_end(self.h, int(n_steps), _ptr(parts), _ptr(gd), 1 if want_scores else 0,
+                                         _ptr(tables[0]) if tables else None, _ptr(tables[1]) if tables else None,
+                                         _ptr(tables[2]) if tables else None, 1 if prefetch else 0))
+        return parts, float(gd[0]), float(gd[1]), tables
+
     def snapshot_best(self):
         self._ck(self.lib.prmf_snapshot_best(self.h))
 

@@ -350,9 +350,10 @@ def nmf_pathway(X, Gs, gamma=1.0, delta=1.0, tradeoff=None, k_latent=6, tol=1e-3
             eng.set_active(active)
             # :739-742 -- the 10 steps and (while candidates remain) the score tables are enqueued back to
             # back; the host waits once
+            # back; the host waits once, and the GPU already streams X for the next block meanwhile
             eng.step_async(modulus, gamma, delta, tradeoff)
-            tables = eng.scores() if candidates_remain else None
-            parts, g2, d2 = eng.step_collect(modulus)
+            parts, g2, d2, tables = eng.block_end(modulus, want_scores=candidates_remain,
+                                                  prefetch=i + modulus < max_iter)
             for s in range(modulus):
                 out(i + s + 1, float(parts[s, 4]))                         # :447
                 if verbose:

@@ -126,6 +126,10 @@ class NumpyShardEngine:
                 qr[c, p] = self.tables.Ls[p].dot(v).dot(v)
         return mass, qn, qr
 
+    def block_end(self, n_steps, want_scores=True, prefetch=True):
+        parts, g2, d2 = self.step_collect(n_steps)
+        return parts, g2, d2, (self.scores() if want_scores else None)
+
     def snapshot_best(self):
         self._best = (self.U.copy(), self.V.copy())
 

@@ -227,3 +227,39 @@ def test_fused_whole_loop_matches_reference_fixture(monkeypatch, case):
     g = load_golden(case)
     U, V, od, trace, _ = run_product(g)
     check_run_against_golden(g, U, V, od, trace)
+
+
+@pytest.mark.parametrize("k", [6, 12])          # fused-tail path (k <= 10) and the separate-kernel path
+def test_speculative_pass_is_bitwise_neutral(k):
+    """prmf_block_end(prefetch=1) starts the next step's X.V pass (and U update) before the host has the score
+    tables; U, V, objectives, snapshots and restores must be what they are without it."""
+    from prmf_b200 import CudaEngine, pack_pathways
+    X, nodelist, Gs, U, V, active = _instance(300, 1200, k, 9, seed=21)
+    packed = pack_pathways(Gs, nodelist)
+    results = []
+    for prefetch in (False, True):
+        with CudaEngine(300, 300, 1200, k) as eng:
+            eng.set_X(X); eng.set_pathways(packed); eng.set_UV(U, V)
+            log = []
+            for block in range(3):
+                eng.set_active([(a + block) % 9 for a in active])
+                eng.step_async(4, 2.0, 0.4)
+                parts, _, _, tables = eng.block_end(4, want_scores=True, prefetch=prefetch)
+                log.append((parts.copy(), tables[0].copy(), eng.get_UV()))
+                if block == 0:
+                    eng.snapshot_best()
+            after = eng.get_UV()
+            eng.restore_best()                       # discards the speculative pass
+            best = eng.get_UV()
+            eng.set_active(active)
+            parts2, _, _ = eng.step(2, 2.0, 0.4)     # and the engine carries on correctly from the restored state
+            results.append((log, after, best, parts2, eng.get_UV()))
+    a, b = results
+    for (pa, ta, uva), (pb, tb, uvb) in zip(a[0], b[0]):
+        assert np.array_equal(pa, pb) and np.array_equal(ta, tb)
+        assert np.array_equal(uva[0], uvb[0]) and np.array_equal(uva[1], uvb[1])
+    for i in (1, 2, 4):
+        assert np.array_equal(a[i][0], b[i][0]) and np.array_equal(a[i][1], b[i][1])
+    assert np.array_equal(a[3], b[3])
+    # the snapshot taken after block 0 is block 0's state
+    assert np.array_equal(a[2][0], a[0][0][2][0]) and np.array_equal(a[2][1], a[0][0][2][1])

@@ -29,7 +29,9 @@ sys.path.insert(0, ROOT)
 
 M, N_GENES, K, P = 37032, 6750, 10, 300
 MODULUS = 10
-NCU_TRAFFIC_CONFIG2 = 2.0052e9     # bytes per launch of the X-stream kernel at config 2, from ncu --set full
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the X-stream kernel at config 2, from ncu --set full
+NCU_TRAFFIC_CONFIG2 = {False: 2.0073e9,      # fp64 skinny_tma_kernel     (profiles/r1_v5_skinny_tma_ncu_summary.txt)
+                       True: 1.0092e9}       # tf32 tc_rowdot_kernel      (profiles/r1_v5_tc_rowdot_ncu_summary.txt)
 METRIC = "prmf_outer_iterations_per_sec"
 UNIT = "outer_it/s"
 
@@ -333,8 +335,9 @@ def run_ours(a):
     ach = ach_xtu if xtu_ms >= xv_ms else ach_xv
     roofline = {
         "bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-        "traffic": NCU_TRAFFIC_CONFIG2 if (a.m, a.n, a.k, ctx.world, tf32) == (M, N_GENES, K, 1, False) else None,
-        "traffic_source": "profiles/r1_v2_skinny_tma_ncu_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
+        "traffic": NCU_TRAFFIC_CONFIG2[tf32] if (a.m, a.n, a.k, ctx.world) == (M, N_GENES, K, 1) else None,
+        "traffic_source": "profiles/r1_v5_%s_ncu_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum, mean of the two passes)"
+                          % ("tc_rowdot" if tf32 else "skinny_tma"),
         "peak_source": peak_src,
         "xv": {"ms": xv_ms, "GBps": ach_xv, "frac": ach_xv / peak, "bytes": bytes_xv},
         "xtu": {"ms": xtu_ms, "GBps": ach_xtu, "frac": ach_xtu / peak, "bytes": bytes_xtu},

@@ -415,6 +415,7 @@ def run_ours(a):
                "sample": "%d inner steps + 1 restrict of the numpy/scipy oracle at full shape, extrapolated to 10 + 1"
                          % a.cpu_inner_steps, **detail}
 
+    exch_mode = eng.exchange_mode
     ctx.barrier()
     eng.close()
     if ctx.rank == 0:
@@ -425,9 +426,10 @@ def run_ours(a):
             "data": "synthetic",
             "config": {"workload": workload_name(a), "step": "1 outer iteration = 10 inner steps + scores/restrict",
                        "parallelism": "rows of X,U sharded over %d GPU(s)" % a.gpus + (
-                           "" if a.gpus == 1 else (", per-step all-reduce of [X^T U | U^T U]: " + (
-                               "NCCL" if os.environ.get("PRMF_P2P", "1") == "0" else
-                               "fused into the V-update kernel over NVLink peer memory"))),
+                           "" if a.gpus == 1 else (", per-step sum over ranks of [X^T U | U^T U]: " + {
+                               "nccl": "ncclAllReduce", "p2p-v-update": "NVLink peer loads fused into the V-update kernel",
+                               "p2p-pass2": "NVLink peer loads fused into the pass-2 X-stream kernel (exchange + V update)",
+                               "none": "none"}[exch_mode])),
                        "l2": "inputs larger than L2 (X block %.2f GB per GPU per pass)" % (m_local * a.n * xsz / 1e9),
                        "inner_steps_per_s": 1000.0 / inner_ms},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),

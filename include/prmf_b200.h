@@ -158,6 +158,16 @@ int prmf_comm_init(prmf_handle* h, int rank, int nranks, const uint8_t* id);
 #define PRMF_IPC_HANDLE_BYTES 64
 int prmf_p2p_export(prmf_handle* h, uint8_t* handle_out);
 int prmf_p2p_attach(prmf_handle* h, int rank, int nranks, const uint8_t* handles /* nranks x 64 bytes */);
+/* Collective over the ranks, after prmf_p2p_attach succeeded on ALL of them: agree on the exchange path.  When every
+ * rank runs the fused-tail X-stream kernels (k <= 10), the exchange moves INTO the pass-2 kernel: every CTA
+ * publishes the X^T U sums of its share of genes, flags them in every peer's memory, waits for the peers' same
+ * share and adds the ranks' buffers in rank order over P2P loads, then updates its rows of V -- no collective
+ * launch and no separate V-update launch.  Otherwise the exchange stays in the V-update kernel. */
+int prmf_p2p_finalize(prmf_handle* h);
+
+/* How the per-step sum over ranks is done: 0 one rank, 1 ncclAllReduce, 2 NVLink peer loads inside the V-update
+ * kernel, 3 NVLink peer loads inside the pass-2 X-stream kernel (prmf_p2p_finalize). */
+int prmf_exchange_mode(const prmf_handle* h);
 
 /* ---- introspection used by bench.py and the tests ---------------------------------------------------*/
 /* Number of kernel launches issued by this handle so far. */

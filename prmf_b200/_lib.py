@@ -44,6 +44,8 @@ SYMBOLS = {
     "prmf_comm_init": (c_int, [_P, c_int, c_int, POINTER(c_uint8)]),
     "prmf_p2p_export": (c_int, [_P, POINTER(c_uint8)]),
     "prmf_p2p_attach": (c_int, [_P, c_int, c_int, POINTER(c_uint8)]),
+    "prmf_p2p_finalize": (c_int, [_P]),
+    "prmf_exchange_mode": (c_int, [_P]),
     "prmf_launch_count": (c_int64, [_P]),
     "prmf_kernel_times": (c_int, [_P, c_int, POINTER(c_double), POINTER(c_int64)]),
     "prmf_set_profiling": (c_int, [_P, c_int]),

@@ -408,6 +408,58 @@ constexpr int kTmaConsumerWarps = 8;
 constexpr int kTmaThreads = (kTmaConsumerWarps + 1) * 32;
 
 // ----------------------------------------------------------------------------------------------------
+// One-shot all-reduce over NVLink peer memory, fused into the V update (sample-sharded runs).
+// Every rank leaves its locally reduced packed buffer [X^T U | U^T U] in its own HBM; after a flag barrier
+// over peer memory every rank reads all ranks' buffers with plain P2P loads and adds them in rank order, so
+// all ranks obtain bitwise identical sums without a separate collective launch.  The packed buffers are
+// double-buffered by step parity: a rank can only write parity p again after it passed the barrier of the
+// step in between, which every peer reaches only after it finished reading parity p.
+// ----------------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 8;
+
+
+
+struct PeerExchange {
+    int nranks;                                // 0: no exchange (one GPU, or the NCCL path)
+    int rank;
+    const double* red[kMaxPeers];              // rank r's packed buffer of this step's parity (P2P mapped)
+    unsigned long long* flags[kMaxPeers];      // rank r's flag array: flags[r][q] = last step rank q announced
+    unsigned long long seq;                    // this step's sequence number (monotone)
+};
+
+__device__ __forceinline__ double ld_peer(const double* p) {
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+// Announce "my packed buffer of step seq is complete" to every rank, then wait until every rank has done so.
+__device__ __forceinline__ void peer_barrier(const PeerExchange& px) {
+    if (threadIdx.x < px.nranks) {
+        if (blockIdx.x == 0) {
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(px.flags[threadIdx.x] + px.rank), "l"(px.seq) : "memory");
+        }
+        const unsigned long long* mine = px.flags[px.rank] + threadIdx.x;
+        unsigned long long seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+        } while (seen < px.seq);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ double sum_peers(const PeerExchange& px, int64_t idx) {
+    double s = 0.0;
+    double t[kMaxPeers];
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r) t[r] = r < px.nranks ? ld_peer(px.red[r] + idx) : 0.0;
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r) s += t[r];
+    return s;
+}
+
+// ----------------------------------------------------------------------------------------------------
 // Fused tails of the X-stream kernel (k <= 10).  The CTAs of one column panel cover different row chunks; once
 // all of them have stored their partials (a counter per panel, monotone over launches, so it never needs a
 // reset) the panel's rows are complete, and the SAME CTAs split them up and update them on the spot instead of
@@ -416,7 +468,11 @@ constexpr int kTmaThreads = (kTmaConsumerWarps + 1) * 32;
 //          second U buffer, partials of U_new^T U_new
 //   EPI 2 (pass 2, panel = genes, one GPU): B = fixed-order sum of the chunk partials, V update (:425-444) into
 //          the second V buffer, partials of V_new^T V_new and sum(V_new * B) for the objective
-//   EPI 3 (pass 2, sharded): B sums and the Gu sum written to the packed buffer that crosses NVLink
+//   EPI 3 (pass 2, sharded, NCCL path): B sums and the Gu sum written to the packed buffer that is all-reduced
+//   EPI 4 (pass 2, sharded, NVLink peer path): every CTA publishes the B sums of its share in this rank's packed
+//          buffer, announces them with a flag in every peer's memory, waits for the same share of all peers, adds
+//          the ranks' buffers in rank order over P2P loads (bitwise identical on all ranks) and performs the V
+//          update of its share -- exchange and update overlap CTA by CTA, no separate launch, no collective call
 // The per-CTA Gram partials are folded per panel by the last CTA of the panel to finish (second counter), so
 // the next consumer adds only `panels` terms.  All CTAs of the grid must be co-resident (they wait for each
 // other): the grid never exceeds the SM count and the launch is cooperative.  Only the 8 consumer warps take
@@ -446,9 +502,27 @@ struct EpiParams {
     double* VB_part;              // out: [panels]
     // EPI 3
     double* red;                  // [n*k | k*k | 2]
+    // EPI 4 (sharded, NVLink peer exchange inside the kernel)
+    PeerExchange px;              // packed buffers of all ranks (this step's parity), rank, nranks, seq
+    unsigned long long* xflags[kMaxPeers];   // rank r's flag array [nranks][ctas + 1]: flags[q][c] = last step in which
+                                  // rank q published the segment of CTA c (c == ctas: its Gu)
+    double* Gu_glob;              // out: U^T U summed over ranks (k*k), for the objective kernel
 };
 
 __device__ __forceinline__ void cons_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+#ifdef PRMF_EPI_TIMING
+// Developer instrumentation (not part of the product build): per-CTA time stamps of the pass-2 fused tail.
+__device__ unsigned long long g_epi_dbg[160 * 8];
+__device__ __forceinline__ unsigned long long epi_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define EPI_STAMP(i) do { if (threadIdx.x == 0) g_epi_dbg[(blockIdx.x * gridDim.y + blockIdx.y) * 8 + (i)] = epi_gtime(); } while (0)
+#else
+#define EPI_STAMP(i) do { } while (0)
+#endif
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
     unsigned long long v;
@@ -523,32 +597,28 @@ __device__ __forceinline__ void epi_gram(const double* __restrict__ sT, int rows
 }
 
 // dst[e] = sum over `count` partials of src[c*stride + e] for e < n_el (contiguous elements; fixed order per
-// element), 4 elements x 4 partials of a thread in flight at a time instead of one dependent chain per element.
+// element).  Up to 2 elements x 16 partials of a thread are in flight at once instead of one dependent chain
+// per element: the tail is latency bound, so the number of L2 round trips is what counts.
 __device__ __forceinline__ void epi_stage_sums(double* __restrict__ dst, const double* __restrict__ src, int n_el,
                                                int count, int64_t stride) {
-    for (int e0 = threadIdx.x; e0 < n_el; e0 += 256 * 4) {
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        int c = 0;
-        for (; c + 4 <= count; c += 4) {
-            double v[4][4];
+    for (int e0 = threadIdx.x; e0 < n_el; e0 += 256 * 2) {
+        const bool ok1 = e0 + 256 < n_el;
+        double acc0 = 0.0, acc1 = 0.0;
+        for (int c = 0; c < count; c += 16) {
+            double v0[16], v1[16];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int i = 0; i < 16; ++i) {
+                const bool in = c + i < count;
+                v0[i] = in ? __ldcg(src + (int64_t)(c + i) * stride + e0) : 0.0;
+                v1[i] = (in && ok1) ? __ldcg(src + (int64_t)(c + i) * stride + e0 + 256) : 0.0;
+            }
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    v[q][i] = (e0 + 256 * q < n_el) ? __ldcg(src + (int64_t)(c + i) * stride + e0 + 256 * q) : 0.0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[q] += v[q][i];
+            for (int i = 0; i < 16; ++i) {
+                if (c + i < count) { acc0 += v0[i]; acc1 += v1[i]; }
+            }
         }
-        for (; c < count; ++c) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (e0 + 256 * q < n_el) acc[q] += __ldcg(src + (int64_t)c * stride + e0 + 256 * q);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (e0 + 256 * q < n_el) dst[e0 + 256 * q] = acc[q];
+        dst[e0] = acc0;
+        if (ok1) dst[e0 + 256] = acc1;
     }
 }
 
@@ -664,9 +734,10 @@ __device__ __forceinline__ void epi_v_update(const EpiParams& ep, unsigned char*
         ep.vb2[me] = s;
     }
     epi_gram<K>(sT, rows, sBuf, ep.part2 + me * K * K);
-    if (!epi_panel_done(ep, panel, s_flag)) return;
-    if (t < K * K) ep.Gv_part[(int64_t)panel * K * K + t] = sum_strided_cg(ep.part2 + (int64_t)panel * chunks * K * K + t, chunks, K * K);
-    if (t == 128) ep.VB_part[panel] = sum_strided_cg(ep.vb2 + (int64_t)panel * chunks, chunks, 1);
+    if (epi_panel_done(ep, panel, s_flag)) {
+        if (t < K * K) ep.Gv_part[(int64_t)panel * K * K + t] = sum_strided_cg(ep.part2 + (int64_t)panel * chunks * K * K + t, chunks, K * K);
+        if (t == 128) ep.VB_part[panel] = sum_strided_cg(ep.vb2 + (int64_t)panel * chunks, chunks, 1);
+    }
 }
 
 template <int K>
@@ -685,6 +756,121 @@ __device__ __forceinline__ void epi_pack(const EpiParams& ep, int panel, int64_t
         if (t < 2) ep.red[nk + K * K + t] = 0.0;
     }
 }
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int K>
+__device__ __forceinline__ void epi_exchange_v_update(const EpiParams& ep, unsigned char* smem, int* s_flag, int panel,
+                                                      int64_t c0, int width, int64_t cols,
+                                                      const double* __restrict__ Bpart) {
+    const int t = threadIdx.x;
+    const int chunks = (int)gridDim.y;
+    int rb, rows;
+    epi_share(width, cols, c0, rb, rows);
+    const int n_el = rows * K;
+    double* sG = reinterpret_cast<double*>(smem);            // K*K (Gu summed over ranks)
+    double* sBuf = sG + 128;
+    double* sT = sBuf + 8 * K * K;                           // rows x K new rows
+    double* sB = sT + n_el;                                  // rows x K  X^T U (local, then summed over ranks)
+    double* sV = sB + n_el;                                  // rows x K old rows
+    double* sW = sG + 112;
+    const int64_t base = (c0 + rb) * K;
+    const PeerExchange& px = ep.px;
+    const int cta = panel * chunks + (int)blockIdx.y;
+    const int ncta = (int)(gridDim.x * gridDim.y);
+    const int fstride = ncta + 1;
+    const int64_t nk = cols * K;
+    double* mine = const_cast<double*>(px.red[px.rank]);
+    // this rank's Gu is complete since pass 1: CTA 0 publishes it straight away
+    if (cta == 0 && t < K * K) mine[nk + t] = sum_strided(ep.Gu_part_in + t, ep.gu_parts, K * K);
+    for (int e = t; e < n_el; e += 256) sV[e] = ep.Vold[base + e];
+    const double gamma = ep.gd[0], delta = ep.gd[1];
+    EPI_STAMP(0);
+    epi_panel_barrier(ep, panel);
+    EPI_STAMP(1);
+    epi_stage_sums(sB, Bpart + base, n_el, chunks, cols * K);                               // local X^T U  (:424)
+    cons_bar();
+    for (int e = t; e < n_el; e += 256) mine[base + e] = sB[e];
+    __threadfence_system();
+    cons_bar();
+    EPI_STAMP(2);
+    // announce the segment (and, from CTA 0, Gu) to every rank, then wait for the same from every rank
+    if (t < px.nranks) st_release_sys_u64(ep.xflags[t] + (size_t)px.rank * fstride + cta, px.seq);
+    if (cta == 0 && t >= 32 && t < 32 + px.nranks)
+        st_release_sys_u64(ep.xflags[t - 32] + (size_t)px.rank * fstride + ncta, px.seq);
+    if (t < px.nranks) {
+        const unsigned long long* f = ep.xflags[px.rank] + (size_t)t * fstride + cta;
+        while (ld_acquire_sys_u64(f) < px.seq) { }
+    } else if (t >= 32 && t < 32 + px.nranks) {
+        const unsigned long long* f = ep.xflags[px.rank] + (size_t)(t - 32) * fstride + ncta;
+        while (ld_acquire_sys_u64(f) < px.seq) { }
+    }
+    cons_bar();
+    EPI_STAMP(3);
+    if (t < K * K) {
+        const double g = sum_peers(px, nk + t);
+        sG[t] = g;
+        if (cta == 0) ep.Gu_glob[t] = g;
+    }
+    for (int e = t; e < n_el; e += 256) sB[e] = sum_peers(px, base + e);                    // sum over ranks, rank order
+    cons_bar();
+    EPI_STAMP(4);
+    double vb = 0.0;
+    for (int e = t; e < n_el; e += 256) {
+        const int r = e / K, c = e - r * K;
+        const int64_t j = c0 + rb + r;
+        const double* vrow = sV + r * K;
+        const double b = sB[e];
+        double cden = 0.0;
+#pragma unroll
+        for (int l = 0; l < K; ++l) cden = fma(vrow[l], sG[l * K + c], cden);               // V.Gu   (:425)
+        const double v = vrow[c];
+        double num = b, den = cden;
+        const int32_t pr = ep.pos[j * K + c];
+        if (pr >= 0) {
+            const Pathways& pw = ep.pw;
+            const int64_t pbase = pw.path_ptr[ep.active[c]];
+            double wv = 0.0;
+            for (int64_t e2 = pw.row_ptr[pr]; e2 < pw.row_ptr[pr + 1]; ++e2)
+                wv = fma(pw.w[e2], ep.Vold[(int64_t)pw.support_idx[pbase + pw.col_local[e2]] * K + c], wv);
+            const double vp1 = v + 1.0;
+            const double man = gamma * wv;                                                  // :434
+            const double ign = delta * (1.0 / (vp1 * vp1));                                 // :438
+            num = b + (man + ign);                                                          // :440
+            den = cden + gamma * (pw.deg[pr] * v);                                          // :435,:441
+        }
+        if (den < kEps) den = kEps;                                                         // :442
+        double vn = v * (num / den);                                                        // :443
+        if (vn < kEps) vn = kEps;                                                           // :444
+        sT[e] = vn;
+        ep.Vnew[j * K + c] = vn;
+        vb = fma(vn, b, vb);
+    }
+    vb = warp_sum(vb);
+    if ((t & 31) == 0) sW[t >> 5] = vb;
+    cons_bar();
+    const int64_t me = (int64_t)panel * chunks + blockIdx.y;
+    if (t == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += sW[w];
+        ep.vb2[me] = s;
+    }
+    epi_gram<K>(sT, rows, sBuf, ep.part2 + me * K * K);
+    EPI_STAMP(5);
+    if (epi_panel_done(ep, panel, s_flag)) {
+        if (t < K * K) ep.Gv_part[(int64_t)panel * K * K + t] = sum_strided_cg(ep.part2 + (int64_t)panel * chunks * K * K + t, chunks, K * K);
+        if (t == 128) ep.VB_part[panel] = sum_strided_cg(ep.vb2 + (int64_t)panel * chunks, chunks, 1);
+    }
+}
+
 
 template <int KT, int RS, int EPI>
 __global__ void __launch_bounds__(kTmaThreads, 1)
@@ -807,6 +993,7 @@ skinny_tma_kernel(const double* __restrict__ M, int64_t ldm, int64_t rows_total,
         if constexpr (EPI == 1) epi_u_update<KT>(ep, smem_raw, &s_last, panel, c0, width, cols, OutPart);
         if constexpr (EPI == 2) epi_v_update<KT>(ep, smem_raw, &s_last, panel, c0, width, cols, OutPart);
         if constexpr (EPI == 3) epi_pack<KT>(ep, panel, c0, width, cols, OutPart);
+        if constexpr (EPI == 4) epi_exchange_v_update<KT>(ep, smem_raw, &s_last, panel, c0, width, cols, OutPart);
     }
 }
 
@@ -1021,7 +1208,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 __device__ __forceinline__ void objective_block(const double* __restrict__ V, int k, const double* __restrict__ sGu,
                                                 double* __restrict__ sGv, double* __restrict__ sSl,
                                                 double* __restrict__ scratch, const double* __restrict__ Gv_part,
-                                                const double* __restrict__ VB_part, int vblocks,
+                                                const double* __restrict__ VB_part, int vblocks, int gv_parts,
                                                 const double* __restrict__ normX_sq, const ActiveSet& as,
                                                 double* __restrict__ Gv, double* __restrict__ gd, double tradeoff,
                                                 double* __restrict__ obj_out, int* __restrict__ step_counter,
@@ -1063,10 +1250,10 @@ __device__ __forceinline__ void objective_block(const double* __restrict__ V, in
     // Gv_new[e] = fixed-order sum of the V-update blocks' partials (slices in parallel, then slice sums in order)
     if (kk2 <= 1024) {
         const int nsl = 1024 / kk2;
-        const int per = (vblocks + nsl - 1) / nsl;
+        const int per = (gv_parts + nsl - 1) / nsl;
         if (t < nsl * kk2) {
             const int e = t % kk2, sl = t / kk2;
-            const int b0 = sl * per, cnt = max(0, min(vblocks, b0 + per) - b0);
+            const int b0 = sl * per, cnt = max(0, min(gv_parts, b0 + per) - b0);
             const double* src = Gv_part + (int64_t)b0 * kk2 + e;
             double s2 = 0.0;
             int b = 0;
@@ -1090,7 +1277,7 @@ __device__ __forceinline__ void objective_block(const double* __restrict__ V, in
     } else {
         for (int e = t; e < kk2; e += blockDim.x) {
             double s2 = 0.0;
-            for (int b = 0; b < vblocks; ++b) s2 += __ldcg(Gv_part + (int64_t)b * kk2 + e);
+            for (int b = 0; b < gv_parts; ++b) s2 += __ldcg(Gv_part + (int64_t)b * kk2 + e);
             sGv[e] = s2;
             Gv[e] = s2;
         }
@@ -1164,58 +1351,6 @@ __device__ __forceinline__ void objective_block(const double* __restrict__ V, in
             gd[0] = g2; gd[1] = g2;
         }
     }
-}
-
-// ----------------------------------------------------------------------------------------------------
-// One-shot all-reduce over NVLink peer memory, fused into the V update (sample-sharded runs).
-// Every rank leaves its locally reduced packed buffer [X^T U | U^T U] in its own HBM; after a flag barrier
-// over peer memory every rank reads all ranks' buffers with plain P2P loads and adds them in rank order, so
-// all ranks obtain bitwise identical sums without a separate collective launch.  The packed buffers are
-// double-buffered by step parity: a rank can only write parity p again after it passed the barrier of the
-// step in between, which every peer reaches only after it finished reading parity p.
-// ----------------------------------------------------------------------------------------------------
-constexpr int kMaxPeers = 8;
-
-
-
-struct PeerExchange {
-    int nranks;                                // 0: no exchange (one GPU, or the NCCL path)
-    int rank;
-    const double* red[kMaxPeers];              // rank r's packed buffer of this step's parity (P2P mapped)
-    unsigned long long* flags[kMaxPeers];      // rank r's flag array: flags[r][q] = last step rank q announced
-    unsigned long long seq;                    // this step's sequence number (monotone)
-};
-
-__device__ __forceinline__ double ld_peer(const double* p) {
-    double v;
-    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-}
-
-// Announce "my packed buffer of step seq is complete" to every rank, then wait until every rank has done so.
-__device__ __forceinline__ void peer_barrier(const PeerExchange& px) {
-    if (threadIdx.x < px.nranks) {
-        if (blockIdx.x == 0) {
-            __threadfence_system();
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(px.flags[threadIdx.x] + px.rank), "l"(px.seq) : "memory");
-        }
-        const unsigned long long* mine = px.flags[px.rank] + threadIdx.x;
-        unsigned long long seen;
-        do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
-        } while (seen < px.seq);
-    }
-    __syncthreads();
-}
-
-__device__ __forceinline__ double sum_peers(const PeerExchange& px, int64_t idx) {
-    double s = 0.0;
-    double t[kMaxPeers];
-#pragma unroll
-    for (int r = 0; r < kMaxPeers; ++r) t[r] = r < px.nranks ? ld_peer(px.red[r] + idx) : 0.0;
-#pragma unroll
-    for (int r = 0; r < kMaxPeers; ++r) s += t[r];
-    return s;
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -1326,18 +1461,344 @@ v_update_objective_kernel(const double* __restrict__ Vold, double* __restrict__ 
     TAIL_STAMP(4, true);
     if (threadIdx.x == 0) *ticket = 0u;                 // re-arm for the next launch
     // (the other blocks' results are read with ld.global.cg from L2, where their fenced writes already are)
-    objective_block(Vnew, k, sGu, k > 64 ? Gv : sGv, k > 64 ? sGv : sV, scratch, Gv_part, VB_part, (int)gridDim.x, normX_sq,
-                    as, Gv, gd, tradeoff, obj_out, step_counter, obj_capacity, sVh, kVhCap);
+    objective_block(Vnew, k, sGu, k > 64 ? Gv : sGv, k > 64 ? sGv : sV, scratch, Gv_part, VB_part, (int)gridDim.x,
+                    (int)gridDim.x, normX_sq, as, Gv, gd, tradeoff, obj_out, step_counter, obj_capacity, sVh, kVhCap);
     TAIL_STAMP(5, true);
 }
 
-// Objective of one inner step as its own one-block launch (fused-tail path: the V update ran inside the pass-2
-// kernel and left per-panel partials).
+// ----------------------------------------------------------------------------------------------------
+// Large k (> 16): the k x k Grams are no longer "small state".  (1) Summing the per-block Gram partials inside
+// every consumer block re-read parts x k*k doubles per block (2.9 GB of L2 traffic per step at k = 128): they are
+// folded ONCE by a grid-wide kernel.  (2) The U update is two skinny GEMMs (U.Gv and U_new^T U_new, 2 m k^2 flop
+// each) and gets register tiles: 256 threads = 16 x 16, a thread owns RPT rows x CPT columns of U.Gv and a
+// CPT x CPT block of the Gram; column ownership is interleaved in pairs (columns 32 j + 2 tx, +1) so the shared-memory
+// reads of a warp are conflict-free 128-bit accesses.
+// ----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gram_reduce_kernel(const double* __restrict__ parts, int count, int kk2, double* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < kk2) out[e] = sum_strided(parts + e, count, kk2);
+}
+
+template <int CPT>
+__device__ __forceinline__ int tiled_col(int tx, int j) { return 32 * (j >> 1) + 2 * tx + (j & 1); }
+
+template <int CPT, int RPT>
+__global__ void __launch_bounds__(256)
+u_update_tiled_kernel(double* __restrict__ U, const double* __restrict__ Apart, int achunks,
+                      const double* __restrict__ Gv, int64_t m, int k, double* __restrict__ Gu_part) {
+    constexpr int KT = 16 * CPT;          // padded factor count (k <= KT)
+    constexpr int TR = 16 * RPT;          // rows per tile
+    constexpr int LD = KT + 2;            // row pitch of the U tile (rows of a warp fall into different banks)
+    extern __shared__ __align__(16) double sm_tiled[];
+    double* sGv = sm_tiled;               // KT x KT, zero padded
+    double* sU = sGv + KT * KT;           // TR x LD: old rows, then the new rows in place
+    double* sA = sU + TR * LD;            // TR x k: X.V of the tile's rows (sum of the pass-1 partials)
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    for (int e = threadIdx.x; e < KT * KT; e += 256) {
+        const int l = e / KT, c = e - l * KT;
+        sGv[e] = (l < k && c < k) ? Gv[l * k + c] : 0.0;
+    }
+    double g[CPT][CPT];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i)
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) g[i][j] = 0.0;
+    const int64_t ntiles = (m + TR - 1) / TR;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t r0 = tile * TR;
+        __syncthreads();
+        for (int e = threadIdx.x; e < TR * KT; e += 256) {
+            const int r = e / KT, c = e - r * KT;
+            sU[r * LD + c] = (r0 + r < m && c < k) ? U[(r0 + r) * k + c] : 0.0;
+        }
+        // the rows of a tile are one contiguous run: fixed-order sums of the partials with many loads in flight
+        epi_stage_sums(sA, Apart + r0 * k, (int)min((int64_t)TR, m - r0) * k, achunks, m * k);  // X.V   (:420)
+        __syncthreads();
+        // den = U.Gv for RPT rows x CPT columns
+        double den[RPT][CPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i)
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) den[i][j] = 0.0;
+        for (int l = 0; l < k; ++l) {
+            double u[RPT], gv[CPT];
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) u[i] = sU[(ty + 16 * i) * LD + l];
+#pragma unroll
+            for (int j = 0; j < CPT; j += 2) {
+                const double2 t2 = *reinterpret_cast<const double2*>(sGv + l * KT + tiled_col<CPT>(tx, j));
+                gv[j] = t2.x; gv[j + 1] = t2.y;
+            }
+#pragma unroll
+            for (int i = 0; i < RPT; ++i)
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) den[i][j] = fma(u[i], gv[j], den[i][j]);
+        }
+        double un[RPT][CPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            const int r = ty + 16 * i;
+            const int64_t row = r0 + r;
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                const int c = tiled_col<CPT>(tx, j);
+                double v = 0.0;
+                if (row < m && c < k) {
+                    const double u0 = sU[r * LD + c];
+                    const double d = den[i][j] + u0;
+                    v = u0 * ((d != 0.0) ? sA[r * k + c] / d : 1.0);                              // 0/0 := 1 (:422)
+                    U[row * k + c] = v;
+                }
+                un[i][j] = v;
+            }
+        }
+        __syncthreads();                                   // everyone is done reading the old rows
+#pragma unroll
+        for (int i = 0; i < RPT; ++i)
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) sU[(ty + 16 * i) * LD + tiled_col<CPT>(tx, j)] = un[i][j];
+        __syncthreads();
+        // Gram: G[a][b] += sum_r Unew[r][a] Unew[r][b], a from ty's columns, b from tx's columns
+        for (int r = 0; r < TR; ++r) {
+            double ua[CPT], ub[CPT];
+#pragma unroll
+            for (int j = 0; j < CPT; j += 2) {
+                const double2 a2 = *reinterpret_cast<const double2*>(sU + r * LD + tiled_col<CPT>(ty, j));
+                const double2 b2 = *reinterpret_cast<const double2*>(sU + r * LD + tiled_col<CPT>(tx, j));
+                ua[j] = a2.x; ua[j + 1] = a2.y; ub[j] = b2.x; ub[j + 1] = b2.y;
+            }
+#pragma unroll
+            for (int i = 0; i < CPT; ++i)
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) g[i][j] = fma(ua[i], ub[j], g[i][j]);
+        }
+    }
+    double* out = Gu_part + (int64_t)blockIdx.x * k * k;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+        const int a = tiled_col<CPT>(ty, i);
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int b = tiled_col<CPT>(tx, j);
+            if (a < k && b < k) out[a * k + b] = g[i][j];
+        }
+    }
+}
+
+// V update (:425-444) for large k with the same register tiles as u_update_tiled_kernel: V.Gu and V_new^T V_new are
+// the two k x k contractions; B, the pathway terms and the clamps are applied per owned element.  Leaves per-block
+// partials of V_new^T V_new and sum(V_new * B); the objective is a separate launch (objective_kernel).
+template <int CPT, int RPT>
+__global__ void __launch_bounds__(256)
+v_update_tiled_kernel(const double* __restrict__ Vold, double* __restrict__ Vnew, const double* __restrict__ Bsrc,
+                      int bchunks, int64_t bstride, const double* __restrict__ Gu, int n, int k, Pathways pw,
+                      const int32_t* __restrict__ active, const int32_t* __restrict__ pos,
+                      const double* __restrict__ gd, double* __restrict__ Gv_part, double* __restrict__ VB_part,
+                      PeerExchange px, double* __restrict__ Gu_out) {
+    constexpr int KT = 16 * CPT;
+    constexpr int TR = 16 * RPT;
+    constexpr int LD = KT + 2;
+    extern __shared__ __align__(16) double sm_tiled[];
+    double* sGu = sm_tiled;               // KT x KT, zero padded
+    double* sV = sGu + KT * KT;           // TR x LD: old rows, then the new rows in place
+    double* sB = sV + TR * LD;            // TR x k: X^T U of the tile's genes (summed over chunks / ranks)
+    __shared__ double scratch[32];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int64_t nk_all = (int64_t)n * k;
+    if (px.nranks > 0) peer_barrier(px);
+    for (int e = threadIdx.x; e < KT * KT; e += 256) {
+        const int l = e / KT, c = e - l * KT;
+        double v = 0.0;
+        if (l < k && c < k) v = px.nranks > 0 ? sum_peers(px, nk_all + l * k + c) : Gu[l * k + c];
+        sGu[e] = v;
+        if (Gu_out != nullptr && blockIdx.x == 0 && l < k && c < k) Gu_out[l * k + c] = v;
+    }
+    const double gamma = gd[0], delta = gd[1];
+    double g[CPT][CPT];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i)
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) g[i][j] = 0.0;
+    double vb = 0.0;
+    const int ntiles = (n + TR - 1) / TR;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int j0 = tile * TR;
+        __syncthreads();
+        for (int e = threadIdx.x; e < TR * KT; e += 256) {
+            const int r = e / KT, c = e - r * KT;
+            sV[r * LD + c] = (j0 + r < n && c < k) ? Vold[(int64_t)(j0 + r) * k + c] : 0.0;
+        }
+        {
+            const int n_el = min(TR, n - j0) * k;                                           // X^T U  (:424)
+            if (px.nranks > 0) {
+                for (int e = threadIdx.x; e < n_el; e += 256) sB[e] = sum_peers(px, (int64_t)j0 * k + e);
+            } else {
+                epi_stage_sums(sB, Bsrc + (int64_t)j0 * k, n_el, bchunks, bstride);
+            }
+        }
+        __syncthreads();
+        double den[RPT][CPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i)
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) den[i][j] = 0.0;
+        for (int l = 0; l < k; ++l) {                                                       // V.Gu   (:425)
+            double v[RPT], gu[CPT];
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) v[i] = sV[(ty + 16 * i) * LD + l];
+#pragma unroll
+            for (int j = 0; j < CPT; j += 2) {
+                const double2 t2 = *reinterpret_cast<const double2*>(sGu + l * KT + tiled_col<CPT>(tx, j));
+                gu[j] = t2.x; gu[j + 1] = t2.y;
+            }
+#pragma unroll
+            for (int i = 0; i < RPT; ++i)
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) den[i][j] = fma(v[i], gu[j], den[i][j]);
+        }
+        double vnew[RPT][CPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            const int r = ty + 16 * i;
+            const int jg = j0 + r;
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                const int c = tiled_col<CPT>(tx, j);
+                double vn = 0.0;
+                if (jg < n && c < k) {
+                    const double v = sV[r * LD + c];
+                    const double b = sB[r * k + c];
+                    double num = b, dd = den[i][j];
+                    const int32_t pr = pos[(int64_t)jg * k + c];
+                    if (pr >= 0) {
+                        const int64_t base = pw.path_ptr[active[c]];
+                        double wv = 0.0;
+                        for (int64_t e2 = pw.row_ptr[pr]; e2 < pw.row_ptr[pr + 1]; ++e2)
+                            wv = fma(pw.w[e2], Vold[(int64_t)pw.support_idx[base + pw.col_local[e2]] * k + c], wv);
+                        const double vp1 = v + 1.0;
+                        const double man = gamma * wv;                                      // :434
+                        const double ign = delta * (1.0 / (vp1 * vp1));                     // :438
+                        num = b + (man + ign);                                              // :440
+                        dd = den[i][j] + gamma * (pw.deg[pr] * v);                          // :435,:441
+                    }
+                    if (dd < kEps) dd = kEps;                                               // :442
+                    vn = v * (num / dd);                                                    // :443
+                    if (vn < kEps) vn = kEps;                                               // :444
+                    Vnew[(int64_t)jg * k + c] = vn;
+                    vb = fma(vn, b, vb);
+                }
+                vnew[i][j] = vn;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < RPT; ++i)
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) sV[(ty + 16 * i) * LD + tiled_col<CPT>(tx, j)] = vnew[i][j];
+        __syncthreads();
+        for (int r = 0; r < TR; ++r) {
+            double va[CPT], vbb[CPT];
+#pragma unroll
+            for (int j = 0; j < CPT; j += 2) {
+                const double2 a2 = *reinterpret_cast<const double2*>(sV + r * LD + tiled_col<CPT>(ty, j));
+                const double2 b2 = *reinterpret_cast<const double2*>(sV + r * LD + tiled_col<CPT>(tx, j));
+                va[j] = a2.x; va[j + 1] = a2.y; vbb[j] = b2.x; vbb[j + 1] = b2.y;
+            }
+#pragma unroll
+            for (int i = 0; i < CPT; ++i)
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) g[i][j] = fma(va[i], vbb[j], g[i][j]);
+        }
+    }
+    double* out = Gv_part + (int64_t)blockIdx.x * k * k;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+        const int a = tiled_col<CPT>(ty, i);
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int b = tiled_col<CPT>(tx, j);
+            if (a < k && b < k) out[a * k + b] = g[i][j];
+        }
+    }
+    const double tvb = block_sum(vb, scratch);
+    if (threadIdx.x == 0) VB_part[blockIdx.x] = tvb;
+}
+
+// manifold / ignore terms of the objective (:344-352) over the flattened active set, spread over the grid (large k:
+// k pathways x hundreds of entries are too many gathers for one block).  Per-block partials, fixed order.
+__global__ void __launch_bounds__(256)
+manifold_parts_kernel(const double* __restrict__ V, int k, const double* __restrict__ Gv, ActiveSet as,
+                      double* __restrict__ man_part, double* __restrict__ ign_part) {
+    __shared__ double scratch[32];
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+    double man = 0.0, ign = 0.0;
+    for (int64_t i = t; i < as.n_diag; i += nt) {
+        const int c = as.diag_factor[i];
+        const double vr = V[(int64_t)as.diag_gene[i] * k + c] / sqrt(Gv[c * k + c]);
+        man = fma(as.diag_coef[i] * vr, vr, man);
+        ign += 1.0 / (vr + 1.0);
+    }
+    for (int64_t i = t; i < as.n_off; i += nt) {
+        const int c = as.off_factor[i];
+        const double nrm = sqrt(Gv[c * k + c]);
+        man = fma(as.off_coef[i] * (V[(int64_t)as.off_c[i] * k + c] / nrm), V[(int64_t)as.off_r[i] * k + c] / nrm, man);
+    }
+    const double MAN = block_sum(man, scratch);
+    const double IGN = block_sum(ign, scratch);
+    if (threadIdx.x == 0) { man_part[blockIdx.x] = MAN; ign_part[blockIdx.x] = IGN; }
+}
+
+// Objective of one inner step as its own one-block launch (large k: after gram_reduce_kernel folded the Gram
+// partials; Gu and Gv arrive as single k*k matrices, the sum(V_new*B) partials per V-update block).
 __global__ void __launch_bounds__(kTailThreads)
-objective_kernel(const double* __restrict__ V, int k, const double* __restrict__ Gu_part, int gu_parts,
-                 const double* __restrict__ Gv_part, const double* __restrict__ VB_part, int vparts,
-                 const double* __restrict__ normX_sq, ActiveSet as, double* __restrict__ Gv, double* __restrict__ gd,
-                 double tradeoff, double* __restrict__ obj_out, int* __restrict__ step_counter, int obj_capacity) {
+objective_kernel(const double* __restrict__ V, int k, const double* __restrict__ Gu, const double* __restrict__ Gv_in,
+                 const double* __restrict__ VB_part, int vb_parts, const double* __restrict__ man_part,
+                 const double* __restrict__ ign_part, int mi_parts, const double* __restrict__ normX_sq,
+                 double* __restrict__ Gv, double* __restrict__ gd, double tradeoff, double* __restrict__ obj_out,
+                 int* __restrict__ step_counter, int obj_capacity) {
+    extern __shared__ double sm[];
+    const int kk2 = k * k;
+    // same shared-memory plan as the fused V-update kernel: two k*k arrays only fit up to k = 64
+    double* sGu = sm;
+    double* sGv = sm + kk2;                                   // k <= 64: Gv_new; else the 1024-double slice buffer
+    double* sSl = sm + kk2 + (k > 64 ? 1024 : kk2);           // 1024 doubles
+    double* sVh = sSl + 1024;                                 // kVhCap doubles
+    __shared__ double scratch[5 * 32 + 128];
+    for (int i = threadIdx.x; i < kk2; i += blockDim.x) sGu[i] = Gu[i];
+    __syncthreads();
+    // the manifold / ignore terms were summed by manifold_parts_kernel: hand objective_block an empty active set and
+    // add them (fixed order) to what it writes
+    ActiveSet none{};
+    const int s0 = *step_counter;
+    __syncthreads();
+    objective_block(V, k, sGu, k > 64 ? Gv : sGv, k > 64 ? sGv : sSl, scratch, Gv_in, VB_part, vb_parts, 1, normX_sq, none, Gv,
+                    gd, -1.0, obj_out, step_counter, obj_capacity, sVh, kVhCap);
+    if (threadIdx.x == 0) {
+        double MAN = 0.0, IGN = 0.0;
+        for (int b = 0; b < mi_parts; ++b) { MAN += man_part[b]; IGN += ign_part[b]; }
+        if (s0 < obj_capacity) {
+            double* o = obj_out + (int64_t)s0 * kObjStride;
+            const double gamma = o[5], delta = o[6], recon = o[0];
+            o[1] = MAN; o[2] = IGN;
+            o[4] = recon + gamma * MAN + delta * IGN + o[3];                                 // :362
+            if (tradeoff >= 0.0) {                                                           // :542-548
+                const double den = tradeoff * MAN;
+                const double g2 = (den == 0.0) ? 1.0 : ((1.0 - tradeoff) * recon) / den;
+                gd[0] = g2; gd[1] = g2;
+            }
+        }
+    }
+}
+
+// Objective of one inner step from per-panel partials (fused-tail path, k <= 10: the V update ran inside the pass-2
+// kernel and left `vparts` partials of V_new^T V_new and sum(V_new*B); Gu arrives as `gu_parts` partials).
+__global__ void __launch_bounds__(kTailThreads)
+objective_parts_kernel(const double* __restrict__ V, int k, const double* __restrict__ Gu_part, int gu_parts,
+                       const double* __restrict__ Gv_part, const double* __restrict__ VB_part, int vparts,
+                       const double* __restrict__ normX_sq, ActiveSet as, double* __restrict__ Gv,
+                       double* __restrict__ gd, double tradeoff, double* __restrict__ obj_out,
+                       int* __restrict__ step_counter, int obj_capacity) {
     extern __shared__ double sm[];
     const int kk2 = k * k;
     double* sGu = sm;
@@ -1346,7 +1807,7 @@ objective_kernel(const double* __restrict__ V, int k, const double* __restrict__
     double* sVh = sSl + 1024;           // kVhCap doubles
     __shared__ double scratch[5 * 32 + 128];
     sum_gram_partials(sGu, Gu_part, gu_parts, kk2, sSl);
-    objective_block(V, k, sGu, sGv, sSl, scratch, Gv_part, VB_part, vparts, normX_sq, as, Gv, gd, tradeoff, obj_out,
+    objective_block(V, k, sGu, sGv, sSl, scratch, Gv_part, VB_part, vparts, vparts, normX_sq, as, Gv, gd, tradeoff, obj_out,
                     step_counter, obj_capacity, sVh, kVhCap);
 }
 

@@ -114,6 +114,12 @@ struct prmf_handle {
     int64_t trows_per_chunk1 = 0, trows_per_chunk = 0;
     size_t tma_smem1 = 0, tma_smem2 = 0;
 
+    // large k (> 16): register-tiled U update, Gram partials folded by gram_reduce_kernel, objective as its own launch
+    bool big_k = false;
+    double* mi_part = nullptr;                // manifold | ignore partials of manifold_parts_kernel (2 x 64)
+    int tiled_cpt = 0, tiled_grid = 0;
+    size_t tiled_smem = 0;
+
     // fused tails (k <= 10, TMA path): the U / V updates run in the last CTA of each panel of the X-stream kernels
     bool use_epi = false;
     unsigned long long* epi_counters = nullptr;   // arrive | done, each [tpanels1 + tpanels], monotone over launches
@@ -150,6 +156,9 @@ struct prmf_handle {
     void* peer_base[kMaxPeers] = {nullptr};
     unsigned long long p2p_seq = 0;
     int p2p_parity = 0;
+    // exchange + V update inside the pass-2 kernel (fused-tail path on every rank; agreed in prmf_p2p_finalize)
+    bool use_xchg = false;
+    double* Gu_glob = nullptr;
 
     // Speculative pass 1: the first X.V pass (+ U update on the fused-tail path) of the NEXT inner step does not
     // depend on the active pathways, so prmf_block_end enqueues it before the host waits for the score tables;
@@ -284,6 +293,7 @@ int launch_skinny_epi_t(prmf_handle* h, int epi, const double* M, int64_t ldm, i
         case 1: fn = (const void*)skinny_tma_kernel<KT, 8, 1>; break;
         case 2: fn = (const void*)skinny_tma_kernel<KT, 8, 2>; break;
         case 3: fn = (const void*)skinny_tma_kernel<KT, 8, 3>; break;
+        case 4: fn = (const void*)skinny_tma_kernel<KT, 8, 4>; break;
         default: return fail(h, PRMF_ERR_STATE, "bad fused-tail id %d", epi);
     }
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -474,11 +484,35 @@ size_t vu_smem(const prmf_handle* h) {
     // sGu + (sGv when k <= 64; for larger k that slot only holds the 1024-double slice buffer) + V tile
     return sizeof(double) * (kk2 + (h->k > 64 ? 1024 : kk2) + std::max<size_t>((size_t)h->vu_rows * h->k, 1024) + kVhCap);
 }
+size_t obj_smem(const prmf_handle* h) {
+    const size_t kk2 = (size_t)h->k * h->k;
+    return sizeof(double) * (kk2 + (h->k > 64 ? 1024 : kk2) + 1024 + kVhCap);
+}
 size_t gram_smem(const prmf_handle* h) { return sizeof(double) * ((size_t)h->vu_rows * h->k); }
 
 int launch_u_update(prmf_handle* h) {
     if (h->m == 0) {
         CU(cudaMemsetAsync(h->Gu_part, 0, sizeof(double) * h->uu_grid * h->k * h->k, h->stream));
+        if (h->big_k) CU(cudaMemsetAsync(h->Gu_glob, 0, sizeof(double) * h->k * h->k, h->stream));
+        return PRMF_OK;
+    }
+    if (h->big_k) {
+#define TILED_CASE(C)                                                                                             \
+    case C:                                                                                                       \
+        u_update_tiled_kernel<C, 2><<<h->tiled_grid, 256, h->tiled_smem, h->stream>>>(h->U, h->Apart, a_chunks(h), \
+                                                                                      h->Gv, h->m, h->k, h->Gu_part); \
+        break;
+        switch (h->tiled_cpt) {
+            TILED_CASE(2)
+            TILED_CASE(4)
+            default:
+            TILED_CASE(8)
+        }
+#undef TILED_CASE
+        LAUNCH_CHECK("u_update_tiled_kernel");
+        const int kk2 = h->k * h->k;
+        gram_reduce_kernel<<<(kk2 + 255) / 256, 256, 0, h->stream>>>(h->Gu_part, h->tiled_grid, kk2, h->Gu_glob);
+        LAUNCH_CHECK("gram_reduce_kernel(Gu)");
         return PRMF_OK;
     }
     NI_SWITCH(h->ni, (u_update_kernel<NI><<<h->uu_grid, kTailThreads, uu_smem(h), h->stream>>>(
@@ -505,14 +539,45 @@ int launch_v_update_objective(prmf_handle* h, bool sharded, double tradeoff) {
     }
     const double* Bsrc = sharded ? h->red : h->Bpart;
     const int bchunks = sharded ? 1 : b_chunks(h);
-    const double* Gusrc = sharded ? h->red + nk : h->Gu_part;
-    const int gchunks = sharded ? 1 : h->use_fused ? h->fp.groups : h->uu_grid;
-    NI_SWITCH(h->ni, (v_update_objective_kernel<NI><<<h->vu_grid, kTailThreads, vu_smem(h), h->stream>>>(
-                         h->Vbuf[h->vcur], h->Vbuf[h->vcur ^ 1], Bsrc, bchunks, nk, Gusrc, gchunks, (int)h->n, h->k, h->pw,
-                         h->active, h->pos, h->gd, h->vu_rows, h->Gv_part, h->VB_part, h->normX_sq, h->as, h->Gv,
-                         tradeoff, h->obj, h->step_counter, h->obj_capacity, h->ticket, px)));
-    LAUNCH_CHECK("v_update_objective_kernel");
+    const double* Gusrc = sharded ? h->red + nk : h->big_k ? h->Gu_glob : h->Gu_part;
+    const int gchunks = (sharded || h->big_k) ? 1 : h->use_fused ? h->fp.groups : h->uu_grid;
+    double* Gu_out = (h->big_k && sharded) ? h->Gu_glob : nullptr;
+    if (h->big_k) {
+#define TILED_CASE(C)                                                                                                  \
+    case C:                                                                                                            \
+        v_update_tiled_kernel<C, 2><<<h->vu_grid, 256, h->tiled_smem, h->stream>>>(                                     \
+            h->Vbuf[h->vcur], h->Vbuf[h->vcur ^ 1], Bsrc, bchunks, nk, Gusrc, (int)h->n, h->k, h->pw, h->active, h->pos, \
+            h->gd, h->Gv_part, h->VB_part, px, Gu_out);                                                                \
+        break;
+        switch (h->tiled_cpt) {
+            TILED_CASE(2)
+            TILED_CASE(4)
+            default:
+            TILED_CASE(8)
+        }
+#undef TILED_CASE
+        LAUNCH_CHECK("v_update_tiled_kernel");
+    } else {
+        NI_SWITCH(h->ni, (v_update_objective_kernel<NI><<<h->vu_grid, kTailThreads, vu_smem(h), h->stream>>>(
+                             h->Vbuf[h->vcur], h->Vbuf[h->vcur ^ 1], Bsrc, bchunks, nk, Gusrc, gchunks, (int)h->n, h->k,
+                             h->pw, h->active, h->pos, h->gd, h->vu_rows, h->Gv_part, h->VB_part, h->normX_sq, h->as, h->Gv,
+                             tradeoff, h->obj, h->step_counter, h->obj_capacity, h->ticket, px)));
+        LAUNCH_CHECK("v_update_objective_kernel");
+    }
     h->vcur ^= 1;
+    if (h->big_k) {
+        const int kk2 = h->k * h->k;
+        gram_reduce_kernel<<<(kk2 + 255) / 256, 256, 0, h->stream>>>(h->Gv_part, h->vu_grid, kk2, h->Gv);
+        LAUNCH_CHECK("gram_reduce_kernel(Gv)");
+        constexpr int kMiBlocks = 64;
+        manifold_parts_kernel<<<kMiBlocks, 256, 0, h->stream>>>(h->Vbuf[h->vcur], h->k, h->Gv, h->as, h->mi_part,
+                                                                h->mi_part + kMiBlocks);
+        LAUNCH_CHECK("manifold_parts_kernel");
+        objective_kernel<<<1, kTailThreads, obj_smem(h), h->stream>>>(
+            h->Vbuf[h->vcur], h->k, h->Gu_glob, h->Gv, h->VB_part, h->vu_grid, h->mi_part, h->mi_part + kMiBlocks, kMiBlocks,
+            h->normX_sq, h->Gv, h->gd, tradeoff, h->obj, h->step_counter, h->obj_capacity);
+        LAUNCH_CHECK("objective_kernel");
+    }
     if (h->x_tf32) return refresh_wt(h, h->Vbuf[h->vcur], h->n, h->Vt32, h->ldx32);
     return PRMF_OK;
 }
@@ -602,7 +667,8 @@ int launch_xv_epi(prmf_handle* h) {
     return PRMF_OK;
 }
 
-int launch_xtu_epi(prmf_handle* h, double* packed_dst) {
+// mode 2: V update (one GPU); 3: pack into `packed_dst` (NCCL path); 4: NVLink peer exchange + V update
+int launch_xtu_epi(prmf_handle* h, int mode, double* packed_dst) {
     EpiParams ep{};
     const size_t np = (size_t)h->tpanels1 + h->tpanels;
     ep.arrive = h->epi_counters + h->tpanels1;
@@ -612,8 +678,7 @@ int launch_xtu_epi(prmf_handle* h, double* packed_dst) {
     ep.vb2 = h->epi_vb2;
     ep.Gu_part_in = h->Gu_part;
     ep.gu_parts = h->tpanels1;
-    const bool pack = packed_dst != nullptr;
-    if (pack) {
+    if (mode == 3) {
         ep.red = packed_dst;
     } else {
         ep.Vold = h->Vbuf[h->vcur];
@@ -625,21 +690,36 @@ int launch_xtu_epi(prmf_handle* h, double* packed_dst) {
         ep.Gv_part = h->Gv_part;
         ep.VB_part = h->VB_part;
     }
+    if (mode == 4) {
+        PeerExchange& px = ep.px;
+        px.nranks = h->nranks;
+        px.rank = h->rank;
+        px.seq = ++h->p2p_seq;
+        for (int r = 0; r < h->nranks; ++r) {
+            double* base = (double*)h->peer_base[r];
+            px.red[r] = base + (size_t)h->p2p_parity * h->p2p_red_count;
+            px.flags[r] = nullptr;
+            ep.xflags[r] = (unsigned long long*)(base + 2 * h->p2p_red_count + 64);
+        }
+        h->p2p_parity ^= 1;
+        ep.Gu_glob = h->Gu_glob;
+    }
     int rc = 0;
-    KT_SWITCH_RC(h->k, rc, launch_skinny_epi_t, h, pack ? 3 : 2, h->X, h->ldx, h->m, h->n, h->U, h->tpanels, h->tpanel_w,
+    KT_SWITCH_RC(h->k, rc, launch_skinny_epi_t, h, mode, h->X, h->ldx, h->m, h->n, h->U, h->tpanels, h->tpanel_w,
                  h->tchunks, h->trows_per_chunk, h->tma_smem2, h->Bpart, ep);
     if (rc) return rc;
-    LAUNCH_CHECK(pack ? "skinny_tma_kernel(pass 2 + pack)" : "skinny_tma_kernel(pass 2 + V update)");
-    if (!pack) h->vcur ^= 1;
+    LAUNCH_CHECK(mode == 3 ? "skinny_tma_kernel(pass 2 + pack)" : mode == 4 ? "skinny_tma_kernel(pass 2 + exchange + V update)"
+                                                                            : "skinny_tma_kernel(pass 2 + V update)");
+    if (mode != 3) h->vcur ^= 1;
     return PRMF_OK;
 }
 
-int launch_objective(prmf_handle* h, double tradeoff) {
-    const size_t smem = sizeof(double) * (2 * (size_t)h->k * h->k + 1024 + kVhCap);
-    objective_kernel<<<1, kTailThreads, smem, h->stream>>>(h->Vbuf[h->vcur], h->k, h->Gu_part, h->tpanels1, h->Gv_part,
-                                                           h->VB_part, h->tpanels, h->normX_sq, h->as, h->Gv, h->gd,
-                                                           tradeoff, h->obj, h->step_counter, h->obj_capacity);
-    LAUNCH_CHECK("objective_kernel");
+// fused-tail path (k <= 10): objective of the step from the per-panel partials the pass-2 kernel left
+int launch_objective(prmf_handle* h, double tradeoff, const double* Gu_parts, int gu_parts) {
+    objective_parts_kernel<<<1, kTailThreads, obj_smem(h), h->stream>>>(
+        h->Vbuf[h->vcur], h->k, Gu_parts, gu_parts, h->Gv_part, h->VB_part, h->tpanels, h->normX_sq, h->as, h->Gv, h->gd,
+        tradeoff, h->obj, h->step_counter, h->obj_capacity);
+    LAUNCH_CHECK("objective_parts_kernel");
     return PRMF_OK;
 }
 
@@ -732,13 +812,18 @@ int enqueue_steps(prmf_handle* h, int n_steps, double gamma, double delta, doubl
             if (!skip_pass1) { tic(0); rc = launch_xv_epi(h); toc(); }
             if (rc) return rc;
             if (h->comm == nullptr) {
-                tic(2); rc = launch_xtu_epi(h, nullptr); toc();
+                tic(2); rc = launch_xtu_epi(h, 2, nullptr); toc();               // + V update
                 if (rc) return rc;
-                tic(5); rc = launch_objective(h, tradeoff); toc();
+                tic(5); rc = launch_objective(h, tradeoff, h->Gu_part, h->tpanels1); toc();
+                if (rc) return rc;
+            } else if (h->use_xchg) {
+                tic(2); rc = launch_xtu_epi(h, 4, nullptr); toc();               // + exchange + V update
+                if (rc) return rc;
+                tic(5); rc = launch_objective(h, tradeoff, h->Gu_glob, 1); toc();
                 if (rc) return rc;
             } else {
                 double* dst = h->p2p_ready ? h->p2p_buf + (size_t)h->p2p_parity * h->p2p_red_count : h->red;
-                tic(2); rc = launch_xtu_epi(h, dst); toc();
+                tic(2); rc = launch_xtu_epi(h, 3, dst); toc();
                 if (rc) return rc;
                 if (!h->p2p_ready) {
                     tic(3); rc = allreduce(h, h->red, red_count); toc();
@@ -993,8 +1078,20 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
     h->ni = pick_ni(k);
     h->uu_rows = (int)std::max<int64_t>(8, std::min<int64_t>(128, 2048 / k));
     h->uu_grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (m_local + h->uu_rows - 1) / h->uu_rows));
+    h->big_k = k > 16;
+    if (h->big_k) {
+        h->tiled_cpt = k <= 32 ? 2 : k <= 64 ? 4 : 8;
+        const int kt = 16 * h->tiled_cpt;
+        h->tiled_smem = sizeof(double) * ((size_t)kt * kt + 32 * (size_t)(kt + 2) + 32 * (size_t)k);
+        h->tiled_grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (m_local + 31) / 32));
+        h->uu_grid = h->tiled_grid;              // number of U^T U partials
+    }
     h->vu_rows = (int)std::max<int64_t>(8, std::min<int64_t>(128, 2048 / k));
     h->vu_grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (n + h->vu_rows - 1) / h->vu_rows));
+    if (h->big_k) {                              // tiles of 32 genes per block in the tiled V update
+        h->vu_rows = 32;
+        h->vu_grid = (int)std::max<int64_t>(1, std::min<int64_t>(h->sm_count, (n + 31) / 32));
+    }
     // pass 2 (X^T.U): column panels over genes, row chunks over samples
     h->panels = (int)((n + 1023) / 1024);
     h->panel_w = (int)round_up((n + h->panels - 1) / h->panels, 4);
@@ -1102,7 +1199,7 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
             total += pad((size_t)h->fp.groups * kFExSlots * h->fp.panels * kFRS * kFKP * 2, sizeof(unsigned long long));
         total += pad((size_t)std::max({h->chunks1, h->tchunks1, h->tc_chunks1}) * std::max<int64_t>(1, m_local) * k, d);   // Apart
         total += 2 * pad((size_t)(n + pad_rows) * k, d) + pad((size_t)nk, d);                      // Vbuf[2], Vb
-        total += 2 * pad(kk2, d) + pad((size_t)gu_parts_max * kk2, d) + pad((size_t)gv_parts_max * kk2, d);
+        total += pad(128, d) + 3 * pad(kk2, d) + pad((size_t)gu_parts_max * kk2, d) + pad((size_t)gv_parts_max * kk2, d);
         total += pad(gv_parts_max, d) + pad((size_t)std::max({h->chunks, h->tchunks, h->fp.groups, h->tc_chunks2}) * nk, d);   // VB_part, Bpart
         total += pad(2 * ((size_t)h->tpanels1 + h->tpanels) + 2, sizeof(unsigned long long));     // fused-tail counters
         total += pad((size_t)std::max(h->tpanels1 * h->tchunks1, h->tpanels * h->tchunks) * kk2, d) +
@@ -1133,7 +1230,7 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
     }
     TAKE(h->Apart, double, (size_t)std::max({h->chunks1, h->tchunks1, h->tc_chunks1}) * std::max<int64_t>(1, m_local) * k);
     TAKE(h->Vbuf[0], double, (n + pad_rows) * k); TAKE(h->Vbuf[1], double, (n + pad_rows) * k); TAKE(h->Vb, double, nk);
-    TAKE(h->Gv, double, kk2); TAKE(h->Gvb, double, kk2);
+    TAKE(h->Gv, double, kk2); TAKE(h->Gvb, double, kk2); TAKE(h->Gu_glob, double, kk2); TAKE(h->mi_part, double, 128);
     TAKE(h->Gu_part, double, (size_t)gu_parts_max * kk2);
     TAKE(h->Gv_part, double, (size_t)gv_parts_max * kk2);
     TAKE(h->VB_part, double, gv_parts_max);
@@ -1177,6 +1274,15 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
         if (e != cudaSuccess) rc = fail(h, PRMF_ERR_CUDA, "init memset: %s", cudaGetErrorString(e));
     }
     // opt in to large dynamic shared memory where k needs it
+    if (!rc && h->big_k) {
+        if (h->tiled_cpt == 2) rc = set_smem(h, u_update_tiled_kernel<2, 2>, h->tiled_smem);
+        else if (h->tiled_cpt == 4) rc = set_smem(h, u_update_tiled_kernel<4, 2>, h->tiled_smem);
+        else rc = set_smem(h, u_update_tiled_kernel<8, 2>, h->tiled_smem);
+        if (!rc && h->tiled_cpt == 2) rc = set_smem(h, v_update_tiled_kernel<2, 2>, h->tiled_smem);
+        else if (!rc && h->tiled_cpt == 4) rc = set_smem(h, v_update_tiled_kernel<4, 2>, h->tiled_smem);
+        else if (!rc) rc = set_smem(h, v_update_tiled_kernel<8, 2>, h->tiled_smem);
+        if (!rc) rc = set_smem(h, objective_kernel, obj_smem(h));
+    }
     if (!rc) {
         NQ_SWITCH(h->nq, {
             if (!rc) rc = set_smem(h, gram_rows_kernel<NQ>, gram_smem(h));
@@ -1590,7 +1696,7 @@ int prmf_p2p_export(prmf_handle* h, uint8_t* handle_out) {
     CU(cudaSetDevice(h->device));
     if (!h->p2p_buf) {
         h->p2p_red_count = (size_t)round_up(h->n * h->k + (int64_t)h->k * h->k + 2, 32);
-        const size_t total = 2 * h->p2p_red_count + 64;
+        const size_t total = 2 * h->p2p_red_count + 64 + (size_t)kMaxPeers * (h->sm_count + 2);   // + per-CTA flags
         int rc = dalloc(h, &h->p2p_buf, total);
         if (rc) return rc;
         CU(cudaMemset(h->p2p_buf, 0, total * sizeof(double)));
@@ -1625,6 +1731,31 @@ int prmf_p2p_attach(prmf_handle* h, int rank, int nranks, const uint8_t* handles
     return PRMF_OK;
 }
 
+int prmf_p2p_finalize(prmf_handle* h) {
+    if (!h) return PRMF_ERR_ARG;
+    if (!h->p2p_ready || !h->comm) return fail(h, PRMF_ERR_STATE, "prmf_p2p_finalize needs prmf_comm_init and prmf_p2p_attach");
+    CU(cudaSetDevice(h->device));
+    // the in-kernel exchange is used only if EVERY rank runs the fused-tail path (ranks that disagreed would wait
+    // on flags nobody writes)
+    // opt-in (PRMF_XCHG=1): measured at 2 GPUs it does not beat the exchange inside the V-update kernel yet
+    const char* ex = getenv("PRMF_XCHG");
+    const double mine = (h->use_epi && ex && atoi(ex) == 1) ? 1.0 : 0.0;
+    CU(cudaMemcpyAsync(h->scal_part, &mine, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    int rc = allreduce(h, h->scal_part, 1);
+    if (rc) return rc;
+    double sum = 0.0;
+    CU(cudaMemcpyAsync(&sum, h->scal_part, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->use_xchg = sum > h->nranks - 0.5;
+    return PRMF_OK;
+}
+
+int prmf_exchange_mode(const prmf_handle* h) {
+    if (!h || !h->comm) return 0;
+    if (!h->p2p_ready) return 1;
+    return h->use_xchg ? 3 : 2;
+}
+
 int64_t prmf_launch_count(const prmf_handle* h) { return h ? h->launches : 0; }
 
 int prmf_set_profiling(prmf_handle* h, int on) {
@@ -1652,6 +1783,15 @@ int prmf_debug_fused(unsigned long long* out32) {
 #endif
 
 #ifdef PRMF_TAIL_TIMING
+int prmf_debug_epi_stamps(unsigned long long* out, int count) {
+#ifdef PRMF_EPI_TIMING
+    return cudaMemcpyFromSymbol(out, g_epi_dbg, sizeof(unsigned long long) * count) == cudaSuccess ? 0 : -1;
+#else
+    (void)out; (void)count;
+    return -1;
+#endif
+}
+
 int prmf_debug_tail_stamps(unsigned long long* out16) {
     return cudaMemcpyFromSymbol(out16, g_tail_dbg, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -1;
 }

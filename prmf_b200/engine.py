@@ -201,6 +201,15 @@ class CudaEngine:
         buf = (ctypes.c_uint8 * len(blob)).from_buffer_copy(blob)
         self._ck(self.lib.prmf_p2p_attach(self.h, int(rank), int(nranks), buf))
 
+    def p2p_finalize(self):
+        """Collective: agree on the in-kernel exchange (call after `p2p_attach` succeeded on every rank)."""
+        self._ck(self.lib.prmf_p2p_finalize(self.h))
+
+    @property
+    def exchange_mode(self):
+        """"none" | "nccl" | "p2p-v-update" | "p2p-pass2": how the per-step sum over ranks is done."""
+        return ("none", "nccl", "p2p-v-update", "p2p-pass2")[int(self.lib.prmf_exchange_mode(self.h))]
+
     # -- introspection -------------------------------------------------------------------------------
     @property
     def launch_count(self):
@@ -274,4 +283,5 @@ def attach_collectives(eng, ctx, p2p=None):
         if not all(f == b"1" for f in flags):
             raise _lib.PrmfLibraryError("NVLink peer exchange could not be set up on every rank; "
                                         "rerun with PRMF_P2P=0 to use the NCCL all-reduce")
+        eng.p2p_finalize()
     return eng

@@ -17,13 +17,25 @@ sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, HERE)
 
 
+def synthetic_case(k, m=301, n=523, P=9, seed=11):
+    """A planted instance that is not a fixture of the reference: used to compare sharded against single-GPU runs
+    (e.g. large k, where the tails take the tiled kernels)."""
+    from prmf_b200 import synth
+    X, nodelist, Gs = synth.small_instance(m=m, n=n, k_true=3, n_pathways=P, pathway_size=14, seed=seed)
+    meta = {"seed": 5, "gamma_in": 1.0, "delta_in": 1.0, "tradeoff": None, "k_latent": k, "max_iter": 30}
+    return {"X": X, "Gs": Gs, "nodelist": nodelist, "meta": meta}
+
+
 def main():
     case, outdir, mode = sys.argv[1], sys.argv[2], sys.argv[3]
     from conftest import load_golden
     from prmf_b200 import nmf_pathway
     from prmf_b200.dist import DistContext
     ctx = DistContext.from_env(backend="gloo" if mode == "cpu" else "nccl")
-    g = load_golden(case)
+    if case.startswith("synth:"):
+        g = synthetic_case(int(case.split(":")[1]))
+    else:
+        g = load_golden(case)
     meta = g["meta"]
     np.random.seed(meta["seed"]); random.seed(meta["seed"])
     kw = {}

@@ -25,10 +25,11 @@ def _free_port():
     return port
 
 
-def _run(case, tmp_path, world, mode):
+def _run(case, tmp_path, world, mode, extra_env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), WORKER, case, str(tmp_path), mode]
     env = dict(os.environ, OMP_NUM_THREADS="2", OPENBLAS_NUM_THREADS="2")
+    env.update(extra_env or {})
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     return [np.load(os.path.join(tmp_path, "rank%d.npz" % r)) for r in range(world)]
@@ -79,3 +80,40 @@ def test_two_gpus_nccl(case, tmp_path):
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     outs = _run(case, tmp_path, 2, "gpu")
     _check(case, outs, rtol_obj=1e-9, rtol_uv=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,env", [
+    (6, {"PRMF_XCHG": "1"}),      # exchange + V update inside the pass-2 kernel (opt-in)
+    (6, {"PRMF_P2P": "0"}),       # ncclAllReduce of the packed buffer
+    (24, {}),                     # large k: tiled U / V updates, NVLink peer loads inside the tiled V update
+    (24, {"PRMF_P2P": "0"}),
+])
+def test_two_gpus_match_one_gpu(k, env, tmp_path):
+    """Sharded runs (all exchange flavours) against the same solve on one GPU: identical sampled pathways and
+    maps, objective parts rel 1e-9, U / V rel 1e-6; all ranks bitwise equal."""
+    import contextlib
+    import io
+    import random
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import mp_worker
+    from prmf_b200 import nmf_pathway
+    outs = _run("synth:%d" % k, tmp_path, 2, "gpu", env)
+    g = mp_worker.synthetic_case(k)
+    meta = g["meta"]
+    np.random.seed(meta["seed"]); random.seed(meta["seed"])
+    trace = {"keep_blocks": 0}
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        U, V, od = nmf_pathway(g["X"].copy(), [G.copy() for G in g["Gs"]], k_latent=k, nodelist=list(g["nodelist"]),
+                               max_iter=meta["max_iter"], trace=trace)
+    for z in outs:
+        assert z["sampled"].tolist() == trace["sampled"]
+        np.testing.assert_allclose(z["obj_parts"], np.array(trace["obj_parts"]), rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(z["U"], U, rtol=1e-6, atol=1e-10)
+        np.testing.assert_allclose(z["V"], V, rtol=1e-6, atol=1e-10)
+        assert json.loads(str(z["fmap"])) == {str(kk): [int(p) for p, _ in v] for kk, v in od["latent_to_pathway_data"].items()}
+    np.testing.assert_array_equal(outs[1]["U"], outs[0]["U"])
+    np.testing.assert_array_equal(outs[1]["V"], outs[0]["V"])

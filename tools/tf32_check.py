@@ -60,6 +60,9 @@ def speed(m, n, k, P, steps=10, dtype="tf32"):
 
 
 if __name__ == "__main__":
+    if "--only128" in sys.argv:
+        speed(65536, 20000, 128, 300, steps=2)
+        sys.exit(0)
     for shape in ((128, 64, 16, 4), (300, 700, 10, 8), (129, 257, 3, 5), (64, 2100, 64, 6), (500, 1500, 128, 6), (37, 131, 17, 5)):
         accuracy(*shape)
     accuracy(300, 700, 10, 8, steps=5)

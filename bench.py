@@ -397,14 +397,18 @@ def run_ours(a):
             import contextlib
             import io
             from prmf_b200 import nmf_pathway
-            np.random.seed(1)
-            with contextlib.redirect_stderr(io.StringIO()):
-                t0 = time.perf_counter()
-                nmf_pathway(Xn, list(Gs), k_latent=a.k, nodelist=nodelist, max_iter=16 * MODULUS, quiet=True,
-                            x_dtype=a.x_dtype)
-                dt = time.perf_counter() - t0
-            e2e["whole_solve"] = {"outer_iterations": 16, "seconds": dt, "value": 16 / dt, "unit": UNIT,
-                                  "note": "nmf_pathway(X_host, graphs) -> (U, V) on the host, X uploaded once"}
+            times = []
+            for _ in range(2):                      # the first call also pays one-off costs (lazy kernel loading)
+                np.random.seed(1)
+                with contextlib.redirect_stderr(io.StringIO()):
+                    t0 = time.perf_counter()
+                    nmf_pathway(Xn, list(Gs), k_latent=a.k, nodelist=nodelist, max_iter=16 * MODULUS, quiet=True,
+                                x_dtype=a.x_dtype)
+                    times.append(time.perf_counter() - t0)
+            e2e["whole_solve"] = {"outer_iterations": 16, "seconds": times[1], "seconds_first_call": times[0],
+                                  "value": 16 / times[1], "unit": UNIT,
+                                  "note": "nmf_pathway(X_host, graphs) -> (U, V) on the host, X uploaded once "
+                                          "(engine creation, pathway packing, upload, transposed copy, 16 outer iterations, download)"}
     else:
         Xcpu = None
 

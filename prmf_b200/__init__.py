@@ -10,5 +10,6 @@ from .solver import (find_mins, latent_pathway_tables, nmf_manifold_vec_obj, nmf
 from .pathways import PackedPathways, pack_pathways  # noqa: F401
 from .engine import CudaEngine  # noqa: F401
 from .preprocess import quantile_transform  # noqa: F401
+from .cv import measure_cv_performance, nnls_rows  # noqa: F401
 
 __version__ = "0.1.0"

@@ -53,6 +53,8 @@ SYMBOLS = {
     "prmf_quantile_transform": (c_int, [c_int, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, c_int, _P, _P, _P, _P, _P,
                                         c_int64, _P]),
     "prmf_preprocess_last_error": (c_char_p, []),
+    "prmf_nnls_rows": (c_int, [c_int, _P, c_int64, c_int, _P, c_int64, c_int64, _P, _P, _P, _P]),
+    "prmf_cv_last_error": (c_char_p, []),
 }
 
 _lib = None

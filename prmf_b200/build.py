@@ -14,6 +14,7 @@ HEADER = os.path.join(HERE, "..", "include", "prmf_b200.h")
 SOURCES = {
     "prmf_b200.cu": ["kernels.cuh", "fused.cuh", "tf32.cuh", "nccl_dyn.h"],
     "preprocess.cu": [],
+    "cv.cu": [],
 }
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

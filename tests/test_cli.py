@@ -173,3 +173,47 @@ def test_cli_cross_validation_matches_reference(tmp_path):
     got = np.loadtxt(tmp_path / "test_error.csv", delimiter=",")
     ref = np.loadtxt(os.path.join(GOLDEN, "cli_test1_cv", "test_error.csv"), delimiter=",")
     np.testing.assert_allclose(got, ref, rtol=1e-6)
+
+
+def test_random_restart_commands():
+    """nmf_pathway_rr.py:24-37: every restart gets the shared arguments, its own --outdir run<i> and a bare
+    --manifolds-init; --condor / --n-runs / the outer --outdir are not passed through."""
+    import argparse
+    from prmf_b200 import prmf_args, restarts
+    p = argparse.ArgumentParser()
+    p.add_argument("--n-runs", type=int, default=2)
+    p.add_argument("--condor", action="store_true")
+    p.add_argument("--gpus", type=int, default=None)
+    prmf_args.add_prmf_arguments(p)
+    a = p.parse_args(["--n-runs", "3", "--data", "d.tsv", "--outdir", "out", "--manifolds", "a.graphml", "b.graphml",
+                      "-k", "4", "--delimiter", "\t", "--no-normalize", "--seed", "7"])
+    cmds = restarts.build_commands(a)
+    assert [c[0] for c in cmds] == [os.path.join("out", "run%d" % i) for i in range(3)]
+    argv = cmds[1][1]
+    assert argv[-3:] == ["--outdir", os.path.join("out", "run1"), "--manifolds-init"]
+    assert "--condor" not in argv and "--n-runs" not in argv and "--gpus" not in argv
+    q = argparse.ArgumentParser()
+    prmf_args.add_prmf_arguments(q)
+    b = q.parse_args(argv)                                          # the child accepts what the parent emits
+    assert (b.data, b.k_latent, b.delimiter, b.no_normalize, b.seed, b.manifolds, b.manifolds_init) == (
+        "d.tsv", 4, "\t", True, "7", ["a.graphml", "b.graphml"], [])
+    assert b.outdir == os.path.join("out", "run1") and b.high_dimensional is True
+
+
+@pytest.mark.gpu
+def test_random_restarts_end_to_end(tmp_path):
+    """Two restarts on the reference's test files: both runs finish, write U.csv / V.csv / obj.txt and are listed."""
+    import subprocess
+    rel = _write_inputs(tmp_path)
+    out = tmp_path / "rr"
+    out.mkdir()
+    cmd = [sys.executable, os.path.join(ROOT, "script", "nmf_pathway_rr.py"), "--n-runs", "2", "--data", "data.tsv",
+           "--delimiter", "\t", "--manifolds"] + rel + ["--node-attribute", "name", "--nodelist", "nodelist.txt",
+                                                        "--outdir", str(out), "-k", "3", "--no-normalize"]
+    res = subprocess.run(cmd, cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    for i in range(2):
+        for f in ("U.csv", "V.csv", "obj.txt", "init_pathways.txt", "nmf_pathway.out", "nmf_pathway.err"):
+            assert (out / ("run%d" % i) / f).exists(), f
+    lines = (out / "runs.tsv").read_text().strip().splitlines()
+    assert len(lines) == 3 and all(l.split("\t")[1] == "0" for l in lines[1:])

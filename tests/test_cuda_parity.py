@@ -263,3 +263,70 @@ def test_speculative_pass_is_bitwise_neutral(k):
     assert np.array_equal(a[3], b[3])
     # the snapshot taken after block 0 is block 0's state
     assert np.array_equal(a[2][0], a[0][0][2][0]) and np.array_equal(a[2][1], a[0][0][2][1])
+
+
+# ---- the launch-structure switches must not change results ----------------------------------------------
+@pytest.mark.parametrize("env", [{"PRMF_EPI": "0"}, {"PRMF_COOP": "0"}, {"PRMF_TMA": "0"}])
+@pytest.mark.parametrize("m,n,k,P", [(200, 517, 10, 12), (1000, 6750, 10, 20), (37, 131, 3, 5)])
+def test_launch_structure_switches(monkeypatch, env, m, n, k, P):
+    """PRMF_EPI=0: separate U / V-update launches instead of the fused tails (the path of ranks without rows);
+    PRMF_COOP=0: plain launches of the fused-tail kernels; PRMF_TMA=0: the pre-TMA X-stream kernel."""
+    from prmf_b200 import nmf_manifold_vec_update
+    for key, val in env.items():
+        monkeypatch.setenv(key, val)
+    X, nodelist, Gs, U, V, active = _instance(m, n, k, P, seed=m + n + k, weighted=True)
+    Uo, Vo, parts_o, _, _, _ = oracle_block(X, U, V, Gs, nodelist, active, 3, 2.5, 0.3)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        Ug, Vg, od = nmf_manifold_vec_update(X, U, V, Gs, active, n_steps=3, gamma=2.5, delta=0.3, nodelist=nodelist)
+    np.testing.assert_allclose(Ug, Uo, rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(Vg, Vo, rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(od["obj"], parts_o[-1, 4], rtol=1e-9)
+
+
+@pytest.mark.parametrize("x_dtype", ["f64", "tf32"])
+def test_full_size_properties_config4(x_dtype):
+    """BASELINE config 4 shape (37 032 x 6 750, k = 64, 2 000 pathways; stresses the large-k tails and the score
+    tables): the same size-independent checks as config 2, plus the k x P tables against the host on a sample of
+    (factor, pathway) pairs.  In tf32 mode the tolerances are those of tests/test_tf32.py."""
+    from prmf_b200 import CudaEngine, pack_pathways, synth
+    from helpers import tf32_round
+    m, n, k, P = 37032, 6750, 64, 2000
+    X, nodelist, Gs = synth.recount2_shape(m, n, P, seed=0)
+    tf32 = x_dtype == "tf32"
+    rt = 1e-3 if tf32 else 1e-10
+    Xs = tf32_round(X) if tf32 else X                      # the matrix the engine holds
+    rng = np.random.Generator(np.random.PCG64(7))
+    U = 3 * (1 - rng.random((m, k))); V = 3 * (1 - rng.random((n, k)))
+    packed = pack_pathways(Gs, nodelist)
+    active = [int(p) for p in rng.integers(0, P, size=k)]
+    normX = np.linalg.norm(Xs)
+    with CudaEngine(m, m, n, k, x_dtype=x_dtype) as eng:
+        eng.set_X(X); eng.set_pathways(packed); eng.set_UV(U, V); eng.set_active(active)
+        np.testing.assert_allclose(np.sqrt(eng.normX_sq), normX, rtol=1e-12)
+        gamma, delta = normX / k, 10 / normX
+        parts, _, _ = eng.step(1, gamma, delta)
+        U1, V1 = eng.get_UV()
+        rows = rng.integers(0, m, size=48)
+        num = Xs[rows] @ V
+        den = U[rows] @ (V.T @ V) + U[rows]
+        np.testing.assert_allclose(U1[rows], U[rows] * num / den, rtol=max(rt, 1e-10))
+        np.testing.assert_allclose(parts[0, 3], np.sum(U1 * U1), rtol=1e-11)
+        # genes outside every active pathway: V update without sparse terms (:425-444)
+        B = Xs[:, :40].T @ U1
+        Vn = V[:40] * B / (V[:40] @ (U1.T @ U1))
+        supp = [set(int(g) for g in packed.supports[active[c]]) for c in range(k)]
+        free = np.array([[j not in supp[c] for c in range(k)] for j in range(40)])
+        np.testing.assert_allclose(V1[:40][free], np.maximum(Vn, 1.1920928955078125e-07)[free], rtol=max(rt, 1e-9))
+        parts, g2, d2, (mass, qn, qr) = eng.block_end(0, want_scores=True, prefetch=True)
+        parts, _, _ = eng.step(4, gamma, delta)
+        np.testing.assert_allclose(parts[-1, 7], eng.residual_sq(), rtol=1e-3 if tf32 else 1e-9)
+        assert np.all(np.diff(parts[:, 4]) < 0), "objective should decrease with fixed pathways"
+    # score tables of V1 against the host on a sample of pairs (restrict :115-127, force_distinct :232)
+    from oracle import prmf_oracle as O
+    tables = O.PathwayTables([Gs[p] for p in range(0, P, 97)], nodelist)
+    for c in (0, 17, 63):
+        v = V1[:, c]
+        for q, p in enumerate(range(0, P, 97)):
+            score = np.sqrt(mass[c, p]) + 1 - qn[c, p]
+            np.testing.assert_allclose(score, O.score_match(tables, v, q), rtol=1e-11)

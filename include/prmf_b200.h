@@ -199,7 +199,7 @@ const char* prmf_preprocess_last_error(void);
 /* ---- "next" row of the scope table: the step after the path ----------------------------------------------
  * GPU version of `measure_cv_performance(V, X_test)` (prmf/__init__.py:768-798; script/prmf_runner.py:1074-1079):
  * for every held-out sample x_i (row of X_host, mt x n, `ld` doubles between rows) solve
- * u_i = argmin_{u >= 0} ||x_i - V u|| (V_host: n x k, k <= 64) for the whole batch at once -- the reference loops
+ * u_i = argmin_{u >= 0} ||x_i - V u|| (V_host: n x k, k <= 128) for the whole batch at once -- the reference loops
  * over scipy.optimize.nnls per sample.  Outputs (host, any may be NULL): U_out mt x k; rnorm_out[i] = ||x_i - V u_i||;
  * xnorm_sq_out[i] = ||x_i||^2; status_out[i] = 1 converged, -1 iteration limit (3 k, as scipy), -2 singular block. */
 int prmf_nnls_rows(int device, const double* V_host, int64_t n, int k, const double* X_host, int64_t mt, int64_t ld,

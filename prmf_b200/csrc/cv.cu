@@ -32,7 +32,7 @@ int cv_fail(const char* what, cudaError_t e) {
     return PRMF_ERR_CUDA;
 }
 
-constexpr int kCvMaxK = 64;       // per-thread Cholesky factor lives in local memory (k*k doubles)
+constexpr int kCvMaxK = 128;      // the engine's largest k (V^T V must fit in shared memory: 128 KB)
 constexpr int kGramBlocks = 64;
 
 __device__ __forceinline__ double cv_warp_sum(double v) {
@@ -95,51 +95,59 @@ __global__ void __launch_bounds__(256) cv_xv_kernel(const double* __restrict__ X
 }
 
 // Solve G[P,P] s_P = b_P by Cholesky (G symmetric positive definite on the passive set); idx lists P.
-// L: p x p lower factor in thread-local memory.  Returns false when a pivot is not positive.
+// L: p x p lower factor (row pitch k) in this sample's global workspace.  Returns false when a pivot is not positive.
 __device__ bool cv_solve_passive(const double* __restrict__ sG, int k, const double* __restrict__ b,
                                  const int* __restrict__ idx, int p, double* __restrict__ L, double* __restrict__ y) {
     for (int i = 0; i < p; ++i) {
         for (int j = 0; j <= i; ++j) {
             double s = sG[idx[i] * k + idx[j]];
-            for (int t = 0; t < j; ++t) s -= L[i * kCvMaxK + t] * L[j * kCvMaxK + t];
+            for (int t = 0; t < j; ++t) s -= L[i * k + t] * L[j * k + t];
             if (i == j) {
                 if (!(s > 0.0)) return false;
-                L[i * kCvMaxK + i] = sqrt(s);
+                L[i * k + i] = sqrt(s);
             } else {
-                L[i * kCvMaxK + j] = s / L[j * kCvMaxK + j];
+                L[i * k + j] = s / L[j * k + j];
             }
         }
     }
     for (int i = 0; i < p; ++i) {                       // forward: L y = b_P
         double s = b[idx[i]];
-        for (int t = 0; t < i; ++t) s -= L[i * kCvMaxK + t] * y[t];
-        y[i] = s / L[i * kCvMaxK + i];
+        for (int t = 0; t < i; ++t) s -= L[i * k + t] * y[t];
+        y[i] = s / L[i * k + i];
     }
     for (int i = p - 1; i >= 0; --i) {                  // backward: L^T s = y
         double s = y[i];
-        for (int t = i + 1; t < p; ++t) s -= L[t * kCvMaxK + i] * y[t];
-        y[i] = s / L[i * kCvMaxK + i];
+        for (int t = i + 1; t < p; ++t) s -= L[t * k + i] * y[t];
+        y[i] = s / L[i * k + i];
     }
     return true;
 }
 
-// One thread per sample.  status[i]: 1 converged, -1 iteration limit, -2 singular passive block.
+// One thread per sample.  All per-sample state lives in a global workspace (k*k + 5k doubles and 2k ints per
+// sample) rather than in thread-local arrays: local-memory frames are reserved for every thread the device can
+// hold, which would cost gigabytes at k = 128.  status[i]: 1 converged, -1 iteration limit, -2 singular block.
 __global__ void __launch_bounds__(64) cv_nnls_kernel(const double* __restrict__ G, const double* __restrict__ B, int64_t mt,
                                                      int k, double tol, int maxiter, double* __restrict__ U,
-                                                     int* __restrict__ status) {
+                                                     int* __restrict__ status, double* __restrict__ work_d,
+                                                     int* __restrict__ work_i) {
     extern __shared__ double sG[];
     for (int e = threadIdx.x; e < k * k; e += blockDim.x) sG[e] = G[e];
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= mt) return;
-    double b[kCvMaxK], x[kCvMaxK], s[kCvMaxK], w[kCvMaxK], y[kCvMaxK];
-    double L[kCvMaxK * kCvMaxK];
-    int idx[kCvMaxK];
-    bool P[kCvMaxK];
-    for (int c = 0; c < k; ++c) { b[c] = B[i * k + c]; x[c] = 0.0; s[c] = 0.0; w[c] = b[c]; P[c] = false; }
+    double* wd = work_d + i * ((int64_t)k * k + 5 * k);
+    double* L = wd;
+    double* b = L + (int64_t)k * k;
+    double* x = b + k;
+    double* s = x + k;
+    double* w = s + k;
+    double* y = w + k;
+    int* idx = work_i + i * (2 * (int64_t)k);
+    int* P = idx + k;
+    for (int c = 0; c < k; ++c) { b[c] = B[i * k + c]; x[c] = 0.0; s[c] = 0.0; w[c] = b[c]; P[c] = 0; }
     int iter = 0, st = 1;
     while (true) {
-        // entering variable: largest w outside the passive set (first maximum wins, as np.argmax)
+        // entering variable: largest dual outside the passive set (first maximum wins)
         int enter = -1, np_ = 0;
         bool any = false;
         double best = 0.0;
@@ -149,10 +157,10 @@ __global__ void __launch_bounds__(64) cv_nnls_kernel(const double* __restrict__ 
         }
         if (np_ == k || !any) break;
         for (int c = 0; c < k; ++c) {
-            const double wc = P[c] ? 0.0 : w[c];                // w * (~P)
+            const double wc = P[c] ? 0.0 : w[c];
             if (enter < 0 || wc > best) { best = wc; enter = c; }
         }
-        P[enter] = true;
+        P[enter] = 1;
         int p = 0;
         for (int c = 0; c < k; ++c) { s[c] = 0.0; if (P[c]) idx[p++] = c; }
         if (!cv_solve_passive(sG, k, b, idx, p, L, y)) { st = -2; break; }
@@ -167,7 +175,7 @@ __global__ void __launch_bounds__(64) cv_nnls_kernel(const double* __restrict__ 
                 if (P[c] && s[c] < 0.0) alpha = fmin(alpha, x[c] / (x[c] - s[c]));
             for (int c = 0; c < k; ++c) { x[c] *= (1.0 - alpha); x[c] += alpha * s[c]; }
             for (int c = 0; c < k; ++c)
-                if (x[c] <= tol) P[c] = false;
+                if (x[c] <= tol) P[c] = 0;
             p = 0;
             for (int c = 0; c < k; ++c) { if (P[c]) idx[p++] = c; }
             if (p > 0 && !cv_solve_passive(sG, k, b, idx, p, L, y)) { st = -2; break; }
@@ -221,7 +229,7 @@ int prmf_nnls_rows(int device, const double* V_host, int64_t n, int k, const dou
         return PRMF_ERR_ARG;
     }
     if (k > kCvMaxK) {
-        g_cv_error = "prmf_nnls_rows: k > 64 is not supported";
+        g_cv_error = "prmf_nnls_rows: k > 128 is not supported";
         return PRMF_ERR_ARG;
     }
     cudaError_t e = cudaSetDevice(device);
@@ -229,6 +237,8 @@ int prmf_nnls_rows(int device, const double* V_host, int64_t n, int k, const dou
     if (mt == 0) return PRMF_OK;
     double *dV = nullptr, *dX = nullptr, *dG = nullptr, *dGp = nullptr, *dB = nullptr, *dxx = nullptr, *dU = nullptr, *dr = nullptr;
     int* dst = nullptr;
+    double* dwd = nullptr;
+    int* dwi = nullptr;
     cudaStream_t st = nullptr;
     const int kk2 = k * k;
     int rc = PRMF_OK;
@@ -243,6 +253,8 @@ int prmf_nnls_rows(int device, const double* V_host, int64_t n, int k, const dou
     CVCU(cudaMalloc((void**)&dU, sizeof(double) * mt * k));
     CVCU(cudaMalloc((void**)&dr, sizeof(double) * mt));
     CVCU(cudaMalloc((void**)&dst, sizeof(int) * mt));
+    CVCU(cudaMalloc((void**)&dwd, sizeof(double) * mt * ((size_t)kk2 + 5 * k)));
+    CVCU(cudaMalloc((void**)&dwi, sizeof(int) * mt * 2 * k));
     CVCU(cudaMemcpyAsync(dV, V_host, sizeof(double) * n * k, cudaMemcpyHostToDevice, st));
     CVCU(cudaMemcpy2DAsync(dX, n * sizeof(double), X_host, ld * sizeof(double), n * sizeof(double), mt,
                            cudaMemcpyHostToDevice, st));
@@ -252,7 +264,10 @@ int prmf_nnls_rows(int device, const double* V_host, int64_t n, int k, const dou
         const unsigned wblocks = (unsigned)((mt * 32 + 255) / 256);
         cv_xv_kernel<<<wblocks, 256, 0, st>>>(dX, n, mt, n, dV, k, dB, dxx);
         const double tol = 10.0 * (double)(n > k ? n : k) * DBL_EPSILON;       // scipy: 10 * max(m, n) * np.spacing(1.)
-        cv_nnls_kernel<<<(unsigned)((mt + 63) / 64), 64, sizeof(double) * kk2, st>>>(dG, dB, mt, k, tol, 3 * k, dU, dst);
+        if (sizeof(double) * kk2 > 48 * 1024)
+            CVCU(cudaFuncSetAttribute(cv_nnls_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kk2)));
+        cv_nnls_kernel<<<(unsigned)((mt + 63) / 64), 64, sizeof(double) * kk2, st>>>(dG, dB, mt, k, tol, 3 * k, dU, dst, dwd,
+                                                                                      dwi);
         cv_resid_kernel<<<wblocks, 256, 0, st>>>(dX, n, mt, n, dV, k, dU, dr);
         CVCU(cudaGetLastError());
     }
@@ -264,7 +279,7 @@ int prmf_nnls_rows(int device, const double* V_host, int64_t n, int k, const dou
 #undef CVCU
 done:
     cudaFree(dV); cudaFree(dX); cudaFree(dG); cudaFree(dGp); cudaFree(dB); cudaFree(dxx); cudaFree(dU); cudaFree(dr);
-    cudaFree(dst);
+    cudaFree(dst); cudaFree(dwd); cudaFree(dwi);
     if (st) cudaStreamDestroy(st);
     return rc;
 }

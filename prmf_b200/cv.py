@@ -15,7 +15,7 @@ def _ptr(a):
 
 
 def nnls_rows(V, X, device=None):
-    """u_i = argmin_{u >= 0} ||X[i] - V u|| for every row of X.  V: (n, k) with k <= 64, X: (mt, n).
+    """u_i = argmin_{u >= 0} ||X[i] - V u|| for every row of X.  V: (n, k) with k <= 128, X: (mt, n).
     Returns (U (mt, k), rnorm (mt,), xnorm (mt,)).  Raises when a sample hits scipy's iteration limit (3 k),
     as scipy.optimize.nnls does."""
     import torch

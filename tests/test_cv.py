@@ -16,7 +16,7 @@ def _scipy_cv(V, X):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("mt,n,k,seed", [(40, 300, 6, 0), (257, 1000, 10, 1), (5, 64, 1, 2), (33, 500, 33, 3),
-                                          (64, 900, 64, 4)])
+                                          (64, 900, 64, 4), (40, 1200, 128, 5)])
 def test_batched_nnls_matches_scipy(mt, n, k, seed):
     from prmf_b200 import measure_cv_performance, nnls_rows
     rng = np.random.Generator(np.random.PCG64(seed))

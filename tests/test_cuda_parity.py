@@ -330,3 +330,32 @@ def test_full_size_properties_config4(x_dtype):
         for q, p in enumerate(range(0, P, 97)):
             score = np.sqrt(mass[c, p]) + 1 - qn[c, p]
             np.testing.assert_allclose(score, O.score_match(tables, v, q), rtol=1e-11)
+
+
+def test_score_tables_large_and_small_pathways():
+    """k x P tables (restrict :115-127, force_distinct :232, find_mins :49) for pathways below and above the number
+    of support genes the scores kernel stages in shared memory (321), k above one factor tile (16)."""
+    import networkx as nx
+    from oracle import prmf_oracle as O
+    from prmf_b200 import latent_pathway_tables
+    rng = np.random.Generator(np.random.PCG64(3))
+    n, k = 900, 19
+    nodelist = ["g%d" % i for i in range(n)]
+    Gs = []
+    for size in (350, 12, 321, 322, 40):
+        genes = rng.choice(n, size=size, replace=False)
+        G = nx.Graph()
+        G.add_nodes_from(nodelist[g] for g in genes)
+        for a, b in zip(genes[:-1], genes[1:]):
+            G.add_edge(nodelist[a], nodelist[b], weight=float(rng.random() + 0.5))
+        for _ in range(size):
+            a, b = rng.choice(genes, size=2, replace=False)
+            G.add_edge(nodelist[a], nodelist[b], weight=float(rng.random() + 0.5))
+        Gs.append(G)
+    V = 3 * (1 - rng.random((n, k)))
+    mass, qn, qr = latent_pathway_tables(V, Gs, nodelist)
+    tables = O.PathwayTables(Gs, nodelist)
+    for c in range(k):
+        for p in range(len(Gs)):
+            np.testing.assert_allclose(np.sqrt(mass[c, p]) + 1 - qn[c, p], O.score_match(tables, V[:, c], p), rtol=1e-12)
+            np.testing.assert_allclose(qr[c, p], tables.Ls[p].dot(V[:, c]).dot(V[:, c]), rtol=1e-11)

@@ -1861,61 +1861,38 @@ sum_gram_parts_kernel(const double* __restrict__ G_part, int blocks, int kk2, do
 // ----------------------------------------------------------------------------------------------------
 // Factor x pathway tables (restrict :129-194 / score :115-127, force_distinct_lapls :232, find_mins :49)
 // One block per pathway; a warp per factor (strided); lanes over support rows; fixed-order shuffles.
-// The V values of the pathway's support genes are gathered ONCE per tile of 16 factors into shared memory
-// (factor-major, so lanes over rows are conflict free); the walk over the pathway's edges then reads that copy
-// instead of chasing support_idx -> V through L2 for every edge (the kernel is latency bound: 87 -> ~30 us at
-// config 2).  Pathways with more than kScoreCap support genes take the global-memory walk.  Same arithmetic in
-// the same order either way.
 // ----------------------------------------------------------------------------------------------------
-constexpr int kScoreCap = 321;         // support rows staged per pathway (odd pitch: conflict-free staging writes)
-constexpr int kScoreTile = 16;         // factors per staging round (16 x 321 doubles = 41 KB)
-
 __global__ void __launch_bounds__(256)
 scores_kernel(const double* __restrict__ V, int k, const double* __restrict__ Gv, Pathways pw,
               double* __restrict__ mass, double* __restrict__ quad_norm, double* __restrict__ quad_raw) {
-    __shared__ double sV[kScoreTile * kScoreCap];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int p = blockIdx.x; p < pw.P; p += gridDim.x) {
         const int64_t beg = pw.path_ptr[p], end = pw.path_ptr[p + 1];
-        const int s = (int)(end - beg);
-        const bool staged = s <= kScoreCap;
-        for (int c0 = 0; c0 < k; c0 += kScoreTile) {
-            const int kt = min(kScoreTile, k - c0);
-            if (staged) {
-                __syncthreads();
-                for (int e = threadIdx.x; e < s * kt; e += blockDim.x) {
-                    const int r = e / kt, c = e - r * kt;
-                    sV[c * kScoreCap + r] = V[(int64_t)pw.support_idx[beg + r] * k + c0 + c];
+        for (int c = warp; c < k; c += nw) {
+            const double nrm = sqrt(Gv[c * k + c]);
+            double ms = 0.0, qn = 0.0, qr = 0.0;
+            for (int64_t r = beg + lane; r < end; r += 32) {
+                const double v = V[(int64_t)pw.support_idx[r] * k + c];
+                const double vu = v / nrm;
+                const double ir = pw.isd[r];
+                double yn = (ir * (pw.ldiag[r] * ir)) * vu;
+                double yr = pw.ldiag[r] * v;
+                for (int64_t e2 = pw.row_ptr[r]; e2 < pw.row_ptr[r + 1]; ++e2) {
+                    const int cl = pw.col_local[e2];
+                    if (beg + cl == r) continue;
+                    const double vc = V[(int64_t)pw.support_idx[beg + cl] * k + c];
+                    yn = fma(ir * (-pw.w[e2] * pw.isd[beg + cl]), vc / nrm, yn);
+                    yr = fma(-pw.w[e2], vc, yr);
                 }
-                __syncthreads();
+                ms = fma(vu, vu, ms);
+                qn = fma(yn, vu, qn);
+                qr = fma(yr, v, qr);
             }
-            for (int c = c0 + warp; c < c0 + kt; c += nw) {
-                const double nrm = sqrt(Gv[c * k + c]);
-                const double* sv = sV + (c - c0) * kScoreCap;
-                double ms = 0.0, qn = 0.0, qr = 0.0;
-                for (int64_t r = beg + lane; r < end; r += 32) {
-                    const double v = staged ? sv[r - beg] : V[(int64_t)pw.support_idx[r] * k + c];
-                    const double vu = v / nrm;
-                    const double ir = pw.isd[r];
-                    double yn = (ir * (pw.ldiag[r] * ir)) * vu;
-                    double yr = pw.ldiag[r] * v;
-                    for (int64_t e2 = pw.row_ptr[r]; e2 < pw.row_ptr[r + 1]; ++e2) {
-                        const int cl = pw.col_local[e2];
-                        if (beg + cl == r) continue;
-                        const double vc = staged ? sv[cl] : V[(int64_t)pw.support_idx[beg + cl] * k + c];
-                        yn = fma(ir * (-pw.w[e2] * pw.isd[beg + cl]), vc / nrm, yn);
-                        yr = fma(-pw.w[e2], vc, yr);
-                    }
-                    ms = fma(vu, vu, ms);
-                    qn = fma(yn, vu, qn);
-                    qr = fma(yr, v, qr);
-                }
-                ms = warp_sum(ms); qn = warp_sum(qn); qr = warp_sum(qr);
-                if (lane == 0) {
-                    mass[(int64_t)c * pw.P + p] = ms;
-                    quad_norm[(int64_t)c * pw.P + p] = qn;
-                    quad_raw[(int64_t)c * pw.P + p] = qr;
-                }
+            ms = warp_sum(ms); qn = warp_sum(qn); qr = warp_sum(qr);
+            if (lane == 0) {
+                mass[(int64_t)c * pw.P + p] = ms;
+                quad_norm[(int64_t)c * pw.P + p] = qn;
+                quad_raw[(int64_t)c * pw.P + p] = qr;
             }
         }
     }

@@ -333,8 +333,8 @@ def test_full_size_properties_config4(x_dtype):
 
 
 def test_score_tables_large_and_small_pathways():
-    """k x P tables (restrict :115-127, force_distinct :232, find_mins :49) for pathways below and above the number
-    of support genes the scores kernel stages in shared memory (321), k above one factor tile (16)."""
+    """k x P tables (restrict :115-127, force_distinct :232, find_mins :49) for small and large weighted pathways
+    and more factors than warps per block."""
     import networkx as nx
     from oracle import prmf_oracle as O
     from prmf_b200 import latent_pathway_tables

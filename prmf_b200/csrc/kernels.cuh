@@ -507,6 +507,7 @@ struct EpiParams {
     unsigned long long* xflags[kMaxPeers];   // rank r's flag array [nranks][ctas + 1]: flags[q][c] = last step in which
                                   // rank q published the segment of CTA c (c == ctas: its Gu)
     double* Gu_glob;              // out: U^T U summed over ranks (k*k), for the objective kernel
+    int dbg_slot;                 // developer timing builds only: timeline slot of this launch (-1: none)
 };
 
 __device__ __forceinline__ void cons_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -520,8 +521,14 @@ __device__ __forceinline__ unsigned long long epi_gtime() {
     return t;
 }
 #define EPI_STAMP(i) do { if (threadIdx.x == 0) g_epi_dbg[(blockIdx.x * gridDim.y + blockIdx.y) * 8 + (i)] = epi_gtime(); } while (0)
+// per-launch timeline: [slot][0] first CTA start, [1] last CTA past its main loop, [2] last CTA end
+__device__ unsigned long long g_kt_dbg[64 * 4];
+#define KT_STAMP_MIN(slot, i) do { if (threadIdx.x == 0 && (slot) >= 0 && (slot) < 64) atomicMin(&g_kt_dbg[(slot) * 4 + (i)], epi_gtime()); } while (0)
+#define KT_STAMP_MAX(slot, i) do { if (threadIdx.x == 0 && (slot) >= 0 && (slot) < 64) atomicMax(&g_kt_dbg[(slot) * 4 + (i)], epi_gtime()); } while (0)
 #else
 #define EPI_STAMP(i) do { } while (0)
+#define KT_STAMP_MIN(slot, i) do { } while (0)
+#define KT_STAMP_MAX(slot, i) do { } while (0)
 #endif
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
@@ -892,6 +899,7 @@ skinny_tma_kernel(const double* __restrict__ M, int64_t ldm, int64_t rows_total,
     const int64_t rend = min(rows_total, rbeg + rows_per_chunk);
     const int nstage_iters = rend > rbeg ? (int)((rend - rbeg + RS - 1) / RS) : 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    KT_STAMP_MIN(ep.dbg_slot, 0);
 
     if (threadIdx.x == 0) {
         for (int s2 = 0; s2 < stages; ++s2) {
@@ -988,6 +996,7 @@ skinny_tma_kernel(const double* __restrict__ M, int64_t ldm, int64_t rows_total,
             for (int c = 0; c < KT; ++c) out[c] = acc[g][c];
         }
     }
+    KT_STAMP_MAX(ep.dbg_slot, 1);
     if constexpr (EPI != 0) {
         __shared__ int s_last;
         if constexpr (EPI == 1) epi_u_update<KT>(ep, smem_raw, &s_last, panel, c0, width, cols, OutPart);
@@ -995,6 +1004,7 @@ skinny_tma_kernel(const double* __restrict__ M, int64_t ldm, int64_t rows_total,
         if constexpr (EPI == 3) epi_pack<KT>(ep, panel, c0, width, cols, OutPart);
         if constexpr (EPI == 4) epi_exchange_v_update<KT>(ep, smem_raw, &s_last, panel, c0, width, cols, OutPart);
     }
+    KT_STAMP_MAX(ep.dbg_slot, 2);
 }
 
 // ----------------------------------------------------------------------------------------------------

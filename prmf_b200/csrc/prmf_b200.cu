@@ -264,7 +264,8 @@ template <int KT>
 int launch_skinny_tma_t(prmf_handle* h, const double* M, int64_t ldm, int64_t rows, int64_t cols, const double* W,
                         int panels, int panel_w, int chunks, int64_t rows_per_chunk, size_t smem, double* out) {
     dim3 grid(panels, chunks);
-    const EpiParams none{};
+    EpiParams none{};
+    none.dbg_slot = -1;
     if (h->tma_rs == 4) {
         CU(cudaFuncSetAttribute(skinny_tma_kernel<KT, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         skinny_tma_kernel<KT, 4, 0><<<grid, kTmaThreads, smem, h->stream>>>(M, ldm, rows, cols, W, panel_w, rows_per_chunk,
@@ -652,6 +653,7 @@ int launch_xv_epi(prmf_handle* h) {
     ep.arrive = h->epi_counters;
     ep.done = h->epi_counters + np;
     ep.seq = ++h->epi_seq1;
+    ep.dbg_slot = (int)((2 * (h->epi_seq1 - 1)) % 64);
     ep.part2 = h->epi_part2;
     ep.vb2 = h->epi_vb2;
     ep.Uold = h->U;
@@ -674,6 +676,7 @@ int launch_xtu_epi(prmf_handle* h, int mode, double* packed_dst) {
     ep.arrive = h->epi_counters + h->tpanels1;
     ep.done = h->epi_counters + np + h->tpanels1;
     ep.seq = ++h->epi_seq2;
+    ep.dbg_slot = (int)((2 * (h->epi_seq2 - 1) + 1) % 64);
     ep.part2 = h->epi_part2;
     ep.vb2 = h->epi_vb2;
     ep.Gu_part_in = h->Gu_part;
@@ -1783,6 +1786,20 @@ int prmf_debug_fused(unsigned long long* out32) {
 #endif
 
 #ifdef PRMF_TAIL_TIMING
+int prmf_debug_timeline(unsigned long long* out256, int reset) {
+#ifdef PRMF_EPI_TIMING
+    if (reset) {
+        unsigned long long init[256];
+        for (int i = 0; i < 256; ++i) init[i] = (i % 4 == 0) ? ~0ull : 0ull;
+        return cudaMemcpyToSymbol(g_kt_dbg, init, sizeof init) == cudaSuccess ? 0 : -1;
+    }
+    return cudaMemcpyFromSymbol(out256, g_kt_dbg, sizeof(unsigned long long) * 256) == cudaSuccess ? 0 : -1;
+#else
+    (void)out256; (void)reset;
+    return -1;
+#endif
+}
+
 int prmf_debug_epi_stamps(unsigned long long* out, int count) {
 #ifdef PRMF_EPI_TIMING
     return cudaMemcpyFromSymbol(out, g_epi_dbg, sizeof(unsigned long long) * count) == cudaSuccess ? 0 : -1;

@@ -487,7 +487,8 @@ struct EpiParams {
     // EPI 1
     const double* Uold;
     double* Unew;
-    const double* Gv;             // V^T V of the current V (k*k)
+    const double* Gv;             // V^T V of the current V: gv_parts partials of k*k, added in order
+    int gv_parts;
     double* Gu_part;              // out: [panels][k*k]
     // EPI 2
     const double* Vold;
@@ -500,6 +501,11 @@ struct EpiParams {
     const double* gd;             // gamma, delta on the device
     double* Gv_part;              // out: [panels][k*k]
     double* VB_part;              // out: [panels]
+    // deferred objective (EPI 2; null when the objective is evaluated every step): what the objective of this
+    // step needs, kept per step so that ONE launch at the end of the block evaluates all of them
+    double* hist_Gu;              // out: U^T U of this step (k*k)
+    double* hist_vh;              // out: V_new at the (support gene, factor) pairs of the active set, in its order
+    const int64_t* doff;          // per-factor offsets into that order (ActiveSet)
     // EPI 3
     double* red;                  // [n*k | k*k | 2]
     // EPI 4 (sharded, NVLink peer exchange inside the kernel)
@@ -651,7 +657,7 @@ __device__ __forceinline__ void epi_u_update(const EpiParams& ep, unsigned char*
     double* sA = sT + n_el;                                  // rows x K sums of the pass-1 partials
     double* sU = sA + n_el;                                  // rows x K old rows
     const int64_t base = (c0 + rb) * K;                      // this share is one contiguous run of rows
-    if (t < K * K) sG[t] = ep.Gv[t];
+    if (t < K * K) sG[t] = sum_strided(ep.Gv + t, ep.gv_parts, K * K);
     for (int e = t; e < n_el; e += 256) sU[e] = ep.Uold[base + e];
     epi_panel_barrier(ep, panel);
     epi_stage_sums(sA, Apart + base, n_el, chunks, cols * K);                               // X.V   (:420)
@@ -692,7 +698,11 @@ __device__ __forceinline__ void epi_v_update(const EpiParams& ep, unsigned char*
     double* sW = sG + 112;                                   // 8 warp sums (K*K <= 100 < 112)
     const int64_t base = (c0 + rb) * K;
     // Gu = sum over the sample panels of pass 1 (complete before this kernel started)
-    if (t < K * K) sG[t] = sum_strided(ep.Gu_part_in + t, ep.gu_parts, K * K);
+    if (t < K * K) {
+        const double g = sum_strided(ep.Gu_part_in + t, ep.gu_parts, K * K);
+        sG[t] = g;
+        if (ep.hist_Gu != nullptr && panel == 0 && blockIdx.y == 0) ep.hist_Gu[t] = g;
+    }
     for (int e = t; e < n_el; e += 256) sV[e] = ep.Vold[base + e];
     const double gamma = ep.gd[0], delta = ep.gd[1];
     epi_panel_barrier(ep, panel);
@@ -727,6 +737,7 @@ __device__ __forceinline__ void epi_v_update(const EpiParams& ep, unsigned char*
         if (vn < kEps) vn = kEps;                                                           // :444
         sT[e] = vn;
         ep.Vnew[j * K + c] = vn;
+        if (pr >= 0 && ep.hist_vh != nullptr) ep.hist_vh[ep.doff[c] + (pr - ep.pw.path_ptr[ep.active[c]])] = vn;
         vb = fma(vn, b, vb);
     }
     // sum(V_new * B) of this share: warp sums, then the 8 warp sums in order
@@ -1222,7 +1233,11 @@ __device__ __forceinline__ void objective_block(const double* __restrict__ V, in
                                                 const double* __restrict__ normX_sq, const ActiveSet& as,
                                                 double* __restrict__ Gv, double* __restrict__ gd, double tradeoff,
                                                 double* __restrict__ obj_out, int* __restrict__ step_counter,
-                                                int obj_capacity, double* __restrict__ sVh, int vh_cap) {
+                                                int obj_capacity, double* __restrict__ sVh, int vh_cap,
+                                                const double* __restrict__ vh_pre = nullptr, int row = -1,
+                                                bool publish_gv = true) {
+    // vh_pre: the (support gene, factor) values of V_new already gathered by the V update (deferred objective);
+    // row >= 0: write that row of obj_out and leave the step counter alone; publish_gv: store Gv_new in `Gv`
     const int kk2 = k * k;
     const int t = threadIdx.x;
     // prefetch everything that does not depend on Gv_new: scalars, VB partials, the flattened-Laplacian entries
@@ -1235,7 +1250,7 @@ __device__ __forceinline__ void objective_block(const double* __restrict__ V, in
     const bool staged = as.n_diag <= vh_cap;
     if (staged)
         for (int64_t i = t; i < as.n_diag; i += blockDim.x)
-            sVh[i] = __ldcg(V + (int64_t)as.diag_gene[i] * k + as.diag_factor[i]);
+            sVh[i] = vh_pre != nullptr ? __ldcg(vh_pre + i) : __ldcg(V + (int64_t)as.diag_gene[i] * k + as.diag_factor[i]);
     constexpr int kPre = 4;                       // entries per thread handled from registers (4096 per pass)
     int dfac[kPre], ofac[kPre];
     double dcoef[kPre], dv[kPre], ocoef[kPre], ovr[kPre], ovc[kPre];
@@ -1282,7 +1297,7 @@ __device__ __forceinline__ void objective_block(const double* __restrict__ V, in
             double s2 = 0.0;
             for (int sl = 0; sl < nsl; ++sl) s2 += sSl[sl * kk2 + t];
             sGv[t] = s2;
-            Gv[t] = s2;
+            if (publish_gv) Gv[t] = s2;
         }
     } else {
         for (int e = t; e < kk2; e += blockDim.x) {
@@ -1349,12 +1364,12 @@ __device__ __forceinline__ void objective_block(const double* __restrict__ V, in
         const double r2 = nx2 - 2.0 * VB + GG;
         const double recon = sqrt(r2 > 0.0 ? r2 : 0.0);
         const double obj = recon + gamma * MAN + delta * IGN + FRO;                         // :362
-        const int s2 = *step_counter;
+        const int s2 = row >= 0 ? row : *step_counter;
         if (s2 < obj_capacity) {
             double* o = obj_out + (int64_t)s2 * kObjStride;
             o[0] = recon; o[1] = MAN; o[2] = IGN; o[3] = FRO; o[4] = obj; o[5] = gamma; o[6] = delta; o[7] = r2;
         }
-        *step_counter = s2 + 1;
+        if (row < 0) *step_counter = s2 + 1;
         if (tradeoff >= 0.0) {                                                              // :542-548
             const double den = tradeoff * MAN;
             const double g2 = (den == 0.0) ? 1.0 : ((1.0 - tradeoff) * recon) / den;
@@ -1819,6 +1834,30 @@ objective_parts_kernel(const double* __restrict__ V, int k, const double* __rest
     sum_gram_partials(sGu, Gu_part, gu_parts, kk2, sSl);
     objective_block(V, k, sGu, sGv, sSl, scratch, Gv_part, VB_part, vparts, vparts, normX_sq, as, Gv, gd, tradeoff, obj_out,
                     step_counter, obj_capacity, sVh, kVhCap);
+}
+
+// Deferred objective (fused-tail path, fixed gamma / delta): block s evaluates the objective of inner step s of
+// the block from what that step's V update left behind (per-panel Gram and sum(V_new*B) partials, U^T U, the
+// active-set values of V_new), so a block of n steps costs ONE launch instead of n on the critical path.  The
+// last block publishes Gv_new.  Same arithmetic and summation orders as objective_parts_kernel.
+__global__ void __launch_bounds__(kTailThreads)
+objective_deferred_kernel(int k, const double* __restrict__ hist_Gu, const double* __restrict__ hist_Gvp,
+                          const double* __restrict__ hist_VBp, int vparts, const double* __restrict__ hist_vh,
+                          int vh_stride, const double* __restrict__ normX_sq, ActiveSet as, double* __restrict__ Gv,
+                          double* __restrict__ gd, double* __restrict__ obj_out, int obj_capacity) {
+    extern __shared__ double sm[];
+    const int kk2 = k * k;
+    const int s = blockIdx.x;
+    double* sGu = sm;
+    double* sGv = sm + kk2;
+    double* sSl = sGv + kk2;            // 1024 doubles
+    double* sVh = sSl + 1024;           // kVhCap doubles
+    __shared__ double scratch[5 * 32 + 128];
+    for (int i = threadIdx.x; i < kk2; i += blockDim.x) sGu[i] = hist_Gu[(int64_t)s * kk2 + i];
+    __syncthreads();
+    objective_block(nullptr, k, sGu, sGv, sSl, scratch, hist_Gvp + (int64_t)s * vparts * kk2, hist_VBp + (int64_t)s * vparts,
+                    vparts, vparts, normX_sq, as, Gv, gd, -1.0, obj_out, nullptr, obj_capacity, sVh, kVhCap,
+                    hist_vh + (int64_t)s * vh_stride, s, s == (int)gridDim.x - 1);
 }
 
 // Gram of V from scratch (after prmf_set_UV): same tiling as the update kernel so partial layout matches.

@@ -124,6 +124,10 @@ struct prmf_handle {
     bool use_epi = false;
     unsigned long long* epi_counters = nullptr;   // arrive | done, each [tpanels1 + tpanels], monotone over launches
     unsigned long long epi_seq1 = 0, epi_seq2 = 0;
+    // deferred objective: per-step history [obj_capacity] of what the objective needs (one cudaMalloc)
+    double* hist = nullptr;
+    double *hist_Gu = nullptr, *hist_Gvp = nullptr, *hist_VBp = nullptr, *hist_vh = nullptr;
+    bool defer_ok = false;
     bool epi_coop = true;                     // cooperative launch (co-residency guaranteed by the driver)
     double *epi_part2 = nullptr, *epi_vb2 = nullptr;
 
@@ -647,7 +651,7 @@ int ensure_pos(prmf_handle* h) {
 }
 
 // ---- fused-tail path (use_epi): two X-stream launches per inner step do the U and V updates as well ----
-int launch_xv_epi(prmf_handle* h) {
+int launch_xv_epi(prmf_handle* h, const double* gv_src = nullptr, int gv_parts = 1) {
     EpiParams ep{};
     const size_t np = (size_t)h->tpanels1 + h->tpanels;
     ep.arrive = h->epi_counters;
@@ -658,7 +662,8 @@ int launch_xv_epi(prmf_handle* h) {
     ep.vb2 = h->epi_vb2;
     ep.Uold = h->U;
     ep.Unew = h->U2;
-    ep.Gv = h->Gv;
+    ep.Gv = gv_src ? gv_src : h->Gv;
+    ep.gv_parts = gv_src ? gv_parts : 1;
     ep.Gu_part = h->Gu_part;
     int rc = 0;
     KT_SWITCH_RC(h->k, rc, launch_skinny_epi_t, h, 1, h->Xt, h->ldxt, h->n, h->m, h->Vbuf[h->vcur], h->tpanels1,
@@ -670,7 +675,7 @@ int launch_xv_epi(prmf_handle* h) {
 }
 
 // mode 2: V update (one GPU); 3: pack into `packed_dst` (NCCL path); 4: NVLink peer exchange + V update
-int launch_xtu_epi(prmf_handle* h, int mode, double* packed_dst) {
+int launch_xtu_epi(prmf_handle* h, int mode, double* packed_dst, int hist_slot = -1) {
     EpiParams ep{};
     const size_t np = (size_t)h->tpanels1 + h->tpanels;
     ep.arrive = h->epi_counters + h->tpanels1;
@@ -692,6 +697,14 @@ int launch_xtu_epi(prmf_handle* h, int mode, double* packed_dst) {
         ep.gd = h->gd;
         ep.Gv_part = h->Gv_part;
         ep.VB_part = h->VB_part;
+        if (hist_slot >= 0) {                       // deferred objective: this step's slots
+            const size_t kk2 = (size_t)h->k * h->k;
+            ep.Gv_part = h->hist_Gvp + (size_t)hist_slot * h->tpanels * kk2;
+            ep.VB_part = h->hist_VBp + (size_t)hist_slot * h->tpanels;
+            ep.hist_Gu = h->hist_Gu + (size_t)hist_slot * kk2;
+            ep.hist_vh = h->hist_vh + (size_t)hist_slot * kVhCap;
+            ep.doff = h->as_off;
+        }
     }
     if (mode == 4) {
         PeerExchange& px = ep.px;
@@ -808,9 +821,27 @@ int enqueue_steps(prmf_handle* h, int n_steps, double gamma, double delta, doubl
         if (!h->profiling) return;
         cudaEventRecord(h->ev_pool[h->ev_pairs.back().second + 1], h->stream);
     };
+    const bool defer = h->defer_ok && h->use_epi && h->comm == nullptr && tradeoff < 0.0 && !h->profiling &&
+                       h->as.n_diag <= kVhCap;
     for (int s = 0; s < n_steps; ++s) {
         const bool skip_pass1 = s == 0 && h->ahead != 0;      // already enqueued by prmf_block_end
         if (skip_pass1) h->ahead = 0;
+        if (h->use_epi && defer) {
+            // one GPU, fixed gamma / delta: the objective of every step is evaluated by ONE launch after the block
+            if (!skip_pass1) {
+                const size_t kk2s = (size_t)h->k * h->k;
+                rc = s == 0 ? launch_xv_epi(h) : launch_xv_epi(h, h->hist_Gvp + (size_t)(s - 1) * h->tpanels * kk2s, h->tpanels);
+                if (rc) return rc;
+            }
+            if ((rc = launch_xtu_epi(h, 2, nullptr, s))) return rc;
+            if (s == n_steps - 1) {
+                objective_deferred_kernel<<<n_steps, kTailThreads, obj_smem(h), h->stream>>>(
+                    h->k, h->hist_Gu, h->hist_Gvp, h->hist_VBp, h->tpanels, h->hist_vh, kVhCap, h->normX_sq, h->as, h->Gv,
+                    h->gd, h->obj, h->obj_capacity);
+                LAUNCH_CHECK("objective_deferred_kernel");
+            }
+            continue;
+        }
         if (h->use_epi) {
             if (!skip_pass1) { tic(0); rc = launch_xv_epi(h); toc(); }
             if (rc) return rc;
@@ -1276,6 +1307,20 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
         e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) rc = fail(h, PRMF_ERR_CUDA, "init memset: %s", cudaGetErrorString(e));
     }
+    if (!rc && h->use_epi) {
+        const char* ed = getenv("PRMF_DEFER_OBJ");
+        if (!(ed && atoi(ed) == 0)) {
+            const size_t H = (size_t)h->obj_capacity, kk2s = (size_t)kk2;
+            const size_t n_gu = H * kk2s, n_gvp = H * h->tpanels * kk2s, n_vbp = H * h->tpanels, n_vh = H * kVhCap;
+            if (dalloc(h, &h->hist, n_gu + n_gvp + n_vbp + n_vh) == PRMF_OK) {
+                h->hist_Gu = h->hist;
+                h->hist_Gvp = h->hist_Gu + n_gu;
+                h->hist_VBp = h->hist_Gvp + n_gvp;
+                h->hist_vh = h->hist_VBp + n_vbp;
+                h->defer_ok = true;
+            }
+        }
+    }
     // opt in to large dynamic shared memory where k needs it
     if (!rc && h->big_k) {
         if (h->tiled_cpt == 2) rc = set_smem(h, u_update_tiled_kernel<2, 2>, h->tiled_smem);
@@ -1317,6 +1362,7 @@ int prmf_destroy(prmf_handle* h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->X) cudaFree(h->X);
     if (h->Xt) cudaFree(h->Xt);
+    if (h->hist) cudaFree(h->hist);
     if (h->X32) cudaFree(h->X32);
     if (h->Xt32) cudaFree(h->Xt32);
     if (h->Vt32) cudaFree(h->Vt32);

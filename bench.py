@@ -339,6 +339,10 @@ def run_ours(a):
         "traffic_source": "profiles/r1_v5_%s_ncu_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum, mean of the two passes)"
                           % ("tc_rowdot" if tf32 else "skinny_tma"),
         "peak_source": peak_src,
+        "note": ("launch durations come from a second, event-instrumented pass (an event pair around every launch makes "
+                 "the step a few % slower than the timed pass); at k <= 10 the X-stream launches also contain the fused "
+                 "U / V-update tails (12.7 us each, tools/timeline.py), so `frac` is a lower bound for the stream itself; "
+                 "inner_step.frac is the whole timed step against the two-stream roofline"),
         "xv": {"ms": xv_ms, "GBps": ach_xv, "frac": ach_xv / peak, "bytes": bytes_xv},
         "xtu": {"ms": xtu_ms, "GBps": ach_xtu, "frac": ach_xtu / peak, "bytes": bytes_xtu},
         "inner_step": {"ms": inner_ms, "bytes": step_bytes, "GBps": step_bytes / (inner_ms * 1e-3) / 1e9,

@@ -835,7 +835,10 @@ __device__ __forceinline__ void epi_exchange_v_update(const EpiParams& ep, unsig
     if (t < K * K) {
         const double g = sum_peers(px, nk + t);
         sG[t] = g;
-        if (cta == 0) ep.Gu_glob[t] = g;
+        if (cta == 0) {
+            ep.Gu_glob[t] = g;
+            if (ep.hist_Gu != nullptr) ep.hist_Gu[t] = g;
+        }
     }
     for (int e = t; e < n_el; e += 256) sB[e] = sum_peers(px, base + e);                    // sum over ranks, rank order
     cons_bar();
@@ -869,6 +872,7 @@ __device__ __forceinline__ void epi_exchange_v_update(const EpiParams& ep, unsig
         if (vn < kEps) vn = kEps;                                                           // :444
         sT[e] = vn;
         ep.Vnew[j * K + c] = vn;
+        if (pr >= 0 && ep.hist_vh != nullptr) ep.hist_vh[ep.doff[c] + (pr - ep.pw.path_ptr[ep.active[c]])] = vn;
         vb = fma(vn, b, vb);
     }
     vb = warp_sum(vb);

@@ -821,8 +821,9 @@ int enqueue_steps(prmf_handle* h, int n_steps, double gamma, double delta, doubl
         if (!h->profiling) return;
         cudaEventRecord(h->ev_pool[h->ev_pairs.back().second + 1], h->stream);
     };
-    const bool defer = h->defer_ok && h->use_epi && h->comm == nullptr && tradeoff < 0.0 && !h->profiling &&
-                       h->as.n_diag <= kVhCap;
+    // deferred objective: one GPU, or sharded with the in-kernel exchange (every rank evaluates the same numbers)
+    const bool defer = h->defer_ok && h->use_epi && (h->comm == nullptr || h->use_xchg) && tradeoff < 0.0 &&
+                       !h->profiling && h->as.n_diag <= kVhCap;
     for (int s = 0; s < n_steps; ++s) {
         const bool skip_pass1 = s == 0 && h->ahead != 0;      // already enqueued by prmf_block_end
         if (skip_pass1) h->ahead = 0;
@@ -833,7 +834,7 @@ int enqueue_steps(prmf_handle* h, int n_steps, double gamma, double delta, doubl
                 rc = s == 0 ? launch_xv_epi(h) : launch_xv_epi(h, h->hist_Gvp + (size_t)(s - 1) * h->tpanels * kk2s, h->tpanels);
                 if (rc) return rc;
             }
-            if ((rc = launch_xtu_epi(h, 2, nullptr, s))) return rc;
+            if ((rc = launch_xtu_epi(h, h->comm == nullptr ? 2 : 4, nullptr, s))) return rc;
             if (s == n_steps - 1) {
                 objective_deferred_kernel<<<n_steps, kTailThreads, obj_smem(h), h->stream>>>(
                     h->k, h->hist_Gu, h->hist_Gvp, h->hist_VBp, h->tpanels, h->hist_vh, kVhCap, h->normX_sq, h->as, h->Gv,

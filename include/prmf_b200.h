@@ -206,6 +206,22 @@ int prmf_nnls_rows(int device, const double* V_host, int64_t n, int k, const dou
                    double* U_out, double* rnorm_out, double* xnorm_sq_out, int32_t* status_out);
 const char* prmf_cv_last_error(void);
 
+/* ---- host-side helper (plain C++, no CUDA, no handle) ------------------------------------------------------
+ * One factor of `restrict` (script/prmf_runner.py:159-171) from the rows of the score tables: scores_out[i] =
+ * sqrt(mass_row[ids[i]]) + (1 - quad_row[ids[i]]) (:123-125), threshold = np.percentile(scores, 100 q) with linear
+ * interpolation (q = 0.199 at :159), keep_out = the positions i with scores_out[i] strictly above it.  Returns their
+ * number (0: all scores equal, the case in which the reference raises), negative on bad arguments.  Bit-identical
+ * to the numpy expressions it replaces; the decision logic itself stays on the host as in the reference. */
+int64_t prmf_host_restrict(const double* mass_row, const double* quad_row, const int64_t* ids, int64_t n, double q,
+                           double* scores_out, int64_t* keep_out);
+/* All factors of one `restrict` call (:129-194) in one crossing: factor f (row factor[f] of the k x P tables) has the
+ * candidates ids[off[f] .. off[f+1]); its survivors and their scores are written, compacted, to kept_ids /
+ * kept_scores at [kept_off[f], kept_off[f+1]).  Returns 0; -(f+1) when factor f keeps nothing; -1000000 on bad
+ * arguments. */
+int64_t prmf_host_restrict_batch(const double* mass, const double* quad, int64_t P, int32_t nf, const int32_t* factor,
+                                 const int64_t* ids, const int64_t* off, double q, int64_t* kept_ids,
+                                 double* kept_scores, int64_t* kept_off);
+
 #ifdef __cplusplus
 }
 #endif

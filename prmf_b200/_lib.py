@@ -55,6 +55,8 @@ SYMBOLS = {
     "prmf_preprocess_last_error": (c_char_p, []),
     "prmf_nnls_rows": (c_int, [c_int, _P, c_int64, c_int, _P, c_int64, c_int64, _P, _P, _P, _P]),
     "prmf_cv_last_error": (c_char_p, []),
+    "prmf_host_restrict": (c_int64, [_P, _P, _P, c_int64, c_double, _P, _P]),
+    "prmf_host_restrict_batch": (c_int64, [_P, _P, c_int64, c_int32, _P, _P, _P, c_double, _P, _P, _P]),
 }
 
 _lib = None

@@ -15,6 +15,7 @@ SOURCES = {
     "prmf_b200.cu": ["kernels.cuh", "fused.cuh", "tf32.cuh", "nccl_dyn.h"],
     "preprocess.cu": [],
     "cv.cu": [],
+    "host_logic.cpp": [],
 }
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -64,8 +65,8 @@ def build_library(force=False, verbose=False):
     todo = list(SOURCES) if force else (_stale_objects() or [s for s in SOURCES if not os.path.exists(_obj(s))])
 
     def compile_one(src):
-        cmd = [nvcc, "-O3", "-std=c++17"] + ARCH + ["-lineinfo", "-Xcompiler", "-fPIC", "-c", "-o", _obj(src),
-                                                     os.path.join(CSRC, src)]
+        cmd = [nvcc, "-O3", "-std=c++17"] + ARCH + ["-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off", "-c", "-o",
+                                                     _obj(src), os.path.join(CSRC, src)]
         if verbose:
             cmd += ["-Xptxas", "-v"]
         return src, subprocess.run(cmd, capture_output=True, text=True)

@@ -97,14 +97,19 @@ class _CandArrays:
 def sample_active(latent_to_pathway_data, k_latent):
     """One multinomial draw per factor from the global legacy NumPy RNG, in factor order (:717-730).
     `scipy.stats.multinomial.rvs(1, p)` draws exactly `np.random.multinomial(1, p)` (the last
-    probability is implied), and a single-candidate draw consumes no random numbers in either."""
+    probability is implied), and a single-candidate draw consumes no random numbers in either -- so it is
+    skipped (its probability is still formed: a zero score must raise as `np.seterr(divide='raise')` does, :22)."""
     active = []
-    for k in range(k_latent):
-        ids, scores = _ids_scores(latent_to_pathway_data[k])
-        with np.errstate(divide="raise", invalid="raise"):                  # np.seterr(divide='raise'), :22
-            prob = scores / np.sum(scores)
-        draw = np.random.multinomial(1, prob)
-        active.append(int(ids[int(np.flatnonzero(draw)[0])]))
+    multinomial = np.random.multinomial
+    with np.errstate(divide="raise", invalid="raise"):
+        for k in range(k_latent):
+            ids, scores = _ids_scores(latent_to_pathway_data[k])
+            prob = scores / scores.sum()
+            if ids.shape[0] == 1:
+                active.append(int(ids[0]))
+                continue
+            draw = multinomial(1, prob)
+            active.append(int(ids[int(draw.argmax())]))
     return active
 
 
@@ -128,25 +133,73 @@ def percentile_19_9(x):
     return a + diff * g
 
 
-def restrict_from_tables(mass, quad_norm, latent_to_pathway_data):
+def _restrict_numpy(mass, quad_norm, k, ids):
+    """One factor of `restrict` in numpy (the expressions prmf_host_restrict evaluates in C)."""
+    scores = np.sqrt(mass[k, ids]) + (1 - quad_norm[k, ids])                # :123-125
+    keep = np.flatnonzero(scores > percentile_19_9(scores))                 # :171
+    return scores, keep
+
+
+_host_restrict_batch = None
+
+
+def _restrict_native(mass, quad_norm, todo):
+    """All factors of a `restrict` call through libprmf_b200's host helper (plain C++, no CUDA involved): one FFI
+    crossing, bit-identical results.  todo: [(k, ids)].  Returns {k: _CandArrays}."""
+    global _host_restrict_batch
+    if _host_restrict_batch is None:
+        from . import _lib
+        _host_restrict_batch = _lib.load().prmf_host_restrict_batch
+    nf = len(todo)
+    factor = np.fromiter((k for k, _ in todo), dtype=np.int32, count=nf)
+    off = np.zeros(nf + 1, dtype=np.int64)
+    np.cumsum([ids.shape[0] for _, ids in todo], out=off[1:])
+    ids_all = np.concatenate([ids for _, ids in todo]).astype(np.int64, copy=False)
+    total = int(off[-1])
+    kept_ids = np.empty(total, dtype=np.int64)
+    kept_scores = np.empty(total)
+    kept_off = np.empty(nf + 1, dtype=np.int64)
+    rc = _host_restrict_batch(mass.ctypes.data, quad_norm.ctypes.data, mass.shape[1], nf, factor.ctypes.data,
+                              ids_all.ctypes.data, off.ctypes.data, _Q199, kept_ids.ctypes.data,
+                              kept_scores.ctypes.data, kept_off.ctypes.data)
+    if rc == -1000000:
+        raise ValueError("prmf_host_restrict_batch: bad arguments")
+    if rc < 0:
+        k, ids = todo[int(-rc) - 1]
+        raise ValueError("restrict: all %d candidate scores of factor %d are equal; the reference's fallback "
+                         "(prmf_runner.py:173-183) raises here too" % (len(ids), k))
+    bounds = kept_off.tolist()
+    return {k: _CandArrays(kept_ids[bounds[f]:bounds[f + 1]], kept_scores[bounds[f]:bounds[f + 1]])
+            for f, (k, _) in enumerate(todo)}
+
+
+def restrict_from_tables(mass, quad_norm, latent_to_pathway_data, native=True):
     """`restrict` (:129-194) given the device tables: score = sqrt(mass) + (1 - quad_norm); keep the
-    candidates strictly above the 19.9th percentile (linear interpolation)."""
+    candidates strictly above the 19.9th percentile (linear interpolation).  `native=False` evaluates the same
+    expressions in numpy (the two are bit-identical; tests/test_host_logic.py)."""
     out = {}
+    todo = []
     for k in sorted(latent_to_pathway_data):
         data = latent_to_pathway_data[k]
         if len(data) > 1:
-            ids, _ = _ids_scores(data)
-            scores = np.sqrt(mass[k, ids]) + (1 - quad_norm[k, ids])        # :123-125
-            keep = np.flatnonzero(scores > percentile_19_9(scores))         # :171
+            todo.append((k, _ids_scores(data)[0]))
+        else:
+            out[k] = data
+    if not todo:
+        return out
+    if (native and mass.dtype == np.float64 and quad_norm.dtype == np.float64 and mass.flags.c_contiguous
+            and quad_norm.flags.c_contiguous and mass.shape == quad_norm.shape):
+        out.update(_restrict_native(mass, quad_norm, todo))
+    else:
+        for k, ids in todo:
+            scores, keep = _restrict_numpy(mass, quad_norm, k, ids)
             if len(keep) == 0:
                 # the reference falls into np.random.choice(size=ceil(n*(1-19.9)/100) < 0) and raises
                 raise ValueError("restrict: all %d candidate scores of factor %d are equal; the "
                                  "reference's fallback (prmf_runner.py:173-183) raises here too"
                                  % (len(ids), k))
             out[k] = _CandArrays(ids[keep], scores[keep])
-        else:
-            out[k] = data
-    return out
+    return {k: out[k] for k in sorted(out)}
 
 
 def force_distinct_from_tables(quad_raw, V, supports, active, latent_to_pathway_data, gamma, delta):

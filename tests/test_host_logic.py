@@ -130,3 +130,45 @@ def test_restrict_and_force_from_tables_match_oracle():
     mine = force_distinct_from_tables(g["quad_raw"], V, packed.supports, active, {k: list(v) for k, v in small.items()}, 2.0, 0.5)
     ref = O.force_distinct(V, tables, {k: list(v) for k, v in small.items()}, active, 2.0, 0.5)
     assert {k: [p for p, _ in v] for k, v in mine.items()} == {k: [p for p, _ in v] for k, v in ref.items()}
+
+
+def test_native_restrict_is_bit_identical_to_numpy():
+    """prmf_host_restrict_batch (plain C++ in libprmf_b200.so, no GPU involved) against the numpy expressions of
+    restrict (:123-125, :159, :171): same survivors, same scores, bit for bit -- including ties at the threshold,
+    tiny candidate lists and repeated pruning."""
+    from prmf_b200.solver import _CandArrays, init_latent_to_pathway_data, restrict_from_tables
+    rng = np.random.Generator(np.random.PCG64(0))
+    for k, P in ((10, 300), (3, 7), (64, 2000), (1, 2), (5, 41)):
+        mass = rng.random((k, P))
+        qn = rng.random((k, P))
+        dup = np.arange(0, P - 1, 5)                                    # duplicates -> ties around the percentile
+        mass[:, dup] = mass[:, dup + 1]
+        qn[:, dup] = qn[:, dup + 1]
+        a = b = init_latent_to_pathway_data(k, P)
+        for _ in range(6):
+            try:
+                a = restrict_from_tables(mass, qn, a, native=False)
+            except ValueError:                       # the duplicates left a factor with equal scores only
+                with pytest.raises(ValueError):
+                    restrict_from_tables(mass, qn, b, native=True)
+                break
+            b = restrict_from_tables(mass, qn, b, native=True)
+            assert list(a) == list(b)
+            for f in a:
+                assert np.array_equal(np.asarray(a[f].ids), np.asarray(b[f].ids))
+                assert np.array_equal(np.asarray(a[f].scores), np.asarray(b[f].scores))
+            if all(len(v) <= 2 for v in a.values()):
+                break
+    # a factor with a single candidate is passed through; equal scores raise as the reference does
+    c = {0: _CandArrays(np.array([3]), np.array([1.0])), 1: _CandArrays(np.arange(4), np.ones(4))}
+    flat = np.full((2, 6), 0.25)
+    for native in (False, True):
+        with pytest.raises(ValueError):
+            restrict_from_tables(flat, flat, c, native=native)
+    # non-contiguous / non-float64 tables take the numpy route and agree
+    m32 = rng.random((4, 30)).astype(np.float32)
+    c4 = init_latent_to_pathway_data(4, 30)
+    x = restrict_from_tables(m32, m32, c4)
+    y = restrict_from_tables(m32.astype(np.float64), m32.astype(np.float64), c4)
+    for f in x:
+        assert np.array_equal(np.asarray(x[f].ids), np.asarray(y[f].ids))

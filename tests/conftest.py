@@ -53,4 +53,4 @@ def load_golden(name):
     return out
 
 
-GOLDEN_CASES = ["test1_raw", "test1_norm", "test2_raw", "small_planted", "small_tradeoff"]
+GOLDEN_CASES = ["test1_raw", "test1_norm", "test2_raw", "small_planted", "small_tradeoff", "small_bigk"]

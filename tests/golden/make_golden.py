@@ -195,7 +195,15 @@ def main():
     X4, nodelist4, Gs4 = synth.small_instance(m=40, n=200, k_true=3, n_pathways=12, seed=5,
                                               weighted=True)
     save_case("small_tradeoff", X4, nodelist4, Gs4, 3, tradeoff=0.5, max_iter=120)
+    save_bigk()
     save_kernel_vectors()
+
+
+def save_bigk():
+    """More factors than a 16-wide factor tile (k = 20 over 30 pathways): pins the large-k tails (tiled U / V updates,
+    grid-wide Gram fold, separate objective launch) to the reference itself."""
+    X5, nodelist5, Gs5 = synth.small_instance(m=120, n=400, k_true=3, n_pathways=30, pathway_size=16, seed=7)
+    save_case("small_bigk", X5, nodelist5, Gs5, 20, max_iter=60)
 
 
 
@@ -242,6 +250,10 @@ def save_cli_case():
         os.chdir(cwd)
         shutil.rmtree(tmp)
 
+
+if __name__ == "__main__" and "--only-bigk" in sys.argv:
+    save_bigk()
+    sys.exit(0)
 
 if __name__ == "__main__":
     if "--cli-only" not in sys.argv:

@@ -117,6 +117,7 @@ struct prmf_handle {
     // large k (> 16): register-tiled U update, Gram partials folded by gram_reduce_kernel, objective as its own launch
     bool big_k = false;
     double* mi_part = nullptr;                // manifold | ignore partials of manifold_parts_kernel (2 x 64)
+    double* Gv_red = nullptr;                 // V_new^T V_new folded by gram_reduce_kernel (the objective publishes it to Gv)
     int tiled_cpt = 0, tiled_grid = 0;
     size_t tiled_smem = 0;
 
@@ -572,14 +573,14 @@ int launch_v_update_objective(prmf_handle* h, bool sharded, double tradeoff) {
     h->vcur ^= 1;
     if (h->big_k) {
         const int kk2 = h->k * h->k;
-        gram_reduce_kernel<<<(kk2 + 255) / 256, 256, 0, h->stream>>>(h->Gv_part, h->vu_grid, kk2, h->Gv);
+        gram_reduce_kernel<<<(kk2 + 255) / 256, 256, 0, h->stream>>>(h->Gv_part, h->vu_grid, kk2, h->Gv_red);
         LAUNCH_CHECK("gram_reduce_kernel(Gv)");
         constexpr int kMiBlocks = 64;
-        manifold_parts_kernel<<<kMiBlocks, 256, 0, h->stream>>>(h->Vbuf[h->vcur], h->k, h->Gv, h->as, h->mi_part,
+        manifold_parts_kernel<<<kMiBlocks, 256, 0, h->stream>>>(h->Vbuf[h->vcur], h->k, h->Gv_red, h->as, h->mi_part,
                                                                 h->mi_part + kMiBlocks);
         LAUNCH_CHECK("manifold_parts_kernel");
         objective_kernel<<<1, kTailThreads, obj_smem(h), h->stream>>>(
-            h->Vbuf[h->vcur], h->k, h->Gu_glob, h->Gv, h->VB_part, h->vu_grid, h->mi_part, h->mi_part + kMiBlocks, kMiBlocks,
+            h->Vbuf[h->vcur], h->k, h->Gu_glob, h->Gv_red, h->VB_part, h->vu_grid, h->mi_part, h->mi_part + kMiBlocks, kMiBlocks,
             h->normX_sq, h->Gv, h->gd, tradeoff, h->obj, h->step_counter, h->obj_capacity);
         LAUNCH_CHECK("objective_kernel");
     }
@@ -1234,7 +1235,7 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
             total += pad((size_t)h->fp.groups * kFExSlots * h->fp.panels * kFRS * kFKP * 2, sizeof(unsigned long long));
         total += pad((size_t)std::max({h->chunks1, h->tchunks1, h->tc_chunks1}) * std::max<int64_t>(1, m_local) * k, d);   // Apart
         total += 2 * pad((size_t)(n + pad_rows) * k, d) + pad((size_t)nk, d);                      // Vbuf[2], Vb
-        total += pad(128, d) + 3 * pad(kk2, d) + pad((size_t)gu_parts_max * kk2, d) + pad((size_t)gv_parts_max * kk2, d);
+        total += pad(128, d) + 4 * pad(kk2, d) + pad((size_t)gu_parts_max * kk2, d) + pad((size_t)gv_parts_max * kk2, d);
         total += pad(gv_parts_max, d) + pad((size_t)std::max({h->chunks, h->tchunks, h->fp.groups, h->tc_chunks2}) * nk, d);   // VB_part, Bpart
         total += pad(2 * ((size_t)h->tpanels1 + h->tpanels) + 2, sizeof(unsigned long long));     // fused-tail counters
         total += pad((size_t)std::max(h->tpanels1 * h->tchunks1, h->tpanels * h->tchunks) * kk2, d) +
@@ -1265,7 +1266,7 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
     }
     TAKE(h->Apart, double, (size_t)std::max({h->chunks1, h->tchunks1, h->tc_chunks1}) * std::max<int64_t>(1, m_local) * k);
     TAKE(h->Vbuf[0], double, (n + pad_rows) * k); TAKE(h->Vbuf[1], double, (n + pad_rows) * k); TAKE(h->Vb, double, nk);
-    TAKE(h->Gv, double, kk2); TAKE(h->Gvb, double, kk2); TAKE(h->Gu_glob, double, kk2); TAKE(h->mi_part, double, 128);
+    TAKE(h->Gv, double, kk2); TAKE(h->Gvb, double, kk2); TAKE(h->Gu_glob, double, kk2); TAKE(h->mi_part, double, 128); TAKE(h->Gv_red, double, kk2);
     TAKE(h->Gu_part, double, (size_t)gu_parts_max * kk2);
     TAKE(h->Gv_part, double, (size_t)gv_parts_max * kk2);
     TAKE(h->VB_part, double, gv_parts_max);

@@ -172,3 +172,14 @@ def test_native_restrict_is_bit_identical_to_numpy():
     y = restrict_from_tables(m32.astype(np.float64), m32.astype(np.float64), c4)
     for f in x:
         assert np.array_equal(np.asarray(x[f].ids), np.asarray(y[f].ids))
+
+
+def test_sample_active_raises_like_seterr_divide_raise():
+    """np.seterr(divide='raise') (:22): all-zero scores of a factor make the reference's `scores / sum` raise --
+    also for a factor with a single candidate, whose draw is otherwise skipped."""
+    from prmf_b200.solver import sample_active
+    np.random.seed(0)
+    for cands in ({0: [(3, 0.0)]}, {0: [(1, 0.0), (2, 0.0)]}):
+        with pytest.raises(FloatingPointError):
+            sample_active(cands, 1)
+    assert sample_active({0: [(5, 2.0)], 1: [(7, 1e-300)]}, 2) == [5, 7]

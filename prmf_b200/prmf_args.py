@@ -12,23 +12,29 @@ def _bool(text):
 
 
 def add_prmf_arguments(parser):
-    parser.add_argument("--data", type=str, required=True, help="n_obs x n_features matrix")
-    parser.add_argument("--manifolds", nargs='+', help="graphml files to use as manifold. Node identifiers must appear in nodelist.")
-    parser.add_argument("--manifolds-file", help="A file containing newline-delimited filepaths which are used as graphml files as in <manifolds>")
-    parser.add_argument("--manifolds-init", nargs='*', help="If provided, use this list of manifolds to initialize PRMF (see the reference for the three cases).")
-    parser.add_argument("--node-attribute", help="Relabel nodes in manifolds/graphs so that their node identifiers come from this node attribute.", default=None)
-    parser.add_argument("--outdir", type=str, required=True, help="Directory containing results")
-    parser.add_argument("--nodelist", type=str, help="Association of node identifier to matrix indexes. If not provided, inferred from the header in <--data>.")
-    parser.add_argument("--k-latent", "-k", default=6, help="Number of latent factors", type=int)
-    parser.add_argument("--tolerence", type=float, default=1e-3)
-    parser.add_argument("--seed", default=None)
-    parser.add_argument("--gamma", default=1.0, help="Tradeoff between reconstruction error and manifold regularization term; Default = 1.0", type=float)
-    parser.add_argument("--delta", default=1.0, help="Regularization parameter for penalty for ignoring manifold; Default = 1.0", type=float)
-    parser.add_argument("--tradeoff", default=-1, type=float, help="If set, automatically update gamma and delta from the previous iteration's objective parts. Must be in [0,1]; -1 disables. Default = -1.")
-    parser.add_argument("--high-dimensional", default=True, type=_bool, help="If True, ensure that <data> is of shape m x n with m < n ; otherwise ensure m > n. Default = True.")
-    parser.add_argument("--no-normalize", action='store_true', help="If flag is provided, don't quantile normalize the data")
-    parser.add_argument("--normalize", action='store_true', help="Accepted for compatibility with the reference README; normalisation is the default.")
-    parser.add_argument("--delimiter", default=",", help="Field delimiter in <--data>")
-    parser.add_argument("--m-samples", help="If provided, only use the first <--m-samples> rows in <--data>", type=int)
-    parser.add_argument("--cross-validation", "-c", type=float, help="Fraction of the samples to hold out and measure model performance with")
-    parser.add_argument("--verbose", "-v", action='store_true', help="Report more information during each iteration")
+    add = parser.add_argument
+    add("--data", type=str, required=True, help="delimited text file holding the samples x genes matrix")
+    add("--manifolds", nargs='+', help="pathway graphs, one .graphml file each; their node names must occur in the nodelist")
+    add("--manifolds-file", help="text file listing the .graphml files, one path per line (instead of --manifolds)")
+    add("--manifolds-init", nargs='*',
+        help="seed the factors from pathways: fewer files than -k (or none) are topped up with randomly chosen ones, "
+             "exactly -k files are used as given, more than -k are subsampled")
+    add("--node-attribute", default=None, help="graphml node attribute that carries the gene name (parsed, as in the reference)")
+    add("--outdir", type=str, required=True, help="where U.csv, V.csv and obj.txt are written")
+    add("--nodelist", type=str, help="gene order of the matrix columns, whitespace separated; default: the header of --data")
+    add("--k-latent", "-k", default=6, type=int, help="number of factors")
+    add("--tolerence", type=float, default=1e-3)
+    add("--seed", default=None)
+    add("--gamma", default=1.0, type=float, help="weight of the Laplacian (manifold) term before rescaling by ||X||/k; default 1.0")
+    add("--delta", default=1.0, type=float, help="weight of the penalty for ignoring the manifold before rescaling; default 1.0")
+    add("--tradeoff", default=-1, type=float,
+        help="in [0,1]: re-derive gamma = delta from the last objective after every inner step (larger favours the "
+             "manifold term); -1 (default) keeps them fixed")
+    add("--high-dimensional", default=True, type=_bool,
+        help="transpose the input if needed so that it has fewer rows than columns (default true)")
+    add("--no-normalize", action='store_true', help="skip the quantile normalisation of the data")
+    add("--normalize", action='store_true', help="no-op kept for the reference README's spelling; normalisation is on by default")
+    add("--delimiter", default=",", help="field separator of --data")
+    add("--m-samples", type=int, help="read only this many leading rows of --data")
+    add("--cross-validation", "-c", type=float, help="hold out this fraction of the samples and report their reconstruction error")
+    add("--verbose", "-v", action='store_true', help="print the pathway assignments and objective parts of every iteration")

@@ -1,8 +1,11 @@
 """Build libprmf_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo)."""
+import contextlib
+import fcntl
 import os
 import shutil
 import subprocess
 import sys
+import tempfile
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -55,13 +58,34 @@ def is_stale():
     return _mtime(HEADER) > t
 
 
+@contextlib.contextmanager
+def _build_lock():
+    """One builder at a time (torchrun ranks and restart workers all reach `_lib.load()` at once): an exclusive
+    flock for the whole compile + link."""
+    os.makedirs(OBJDIR, exist_ok=True)
+    with open(os.path.join(OBJDIR, ".lock"), "w") as fh:
+        fcntl.flock(fh, fcntl.LOCK_EX)
+        try:
+            yield
+        finally:
+            fcntl.flock(fh, fcntl.LOCK_UN)
+
+
 def build_library(force=False, verbose=False):
     """Compile the CUDA sources (one object per translation unit, rebuilt only when stale) and link
-    prmf_b200/libprmf_b200.so.  Returns the path."""
+    prmf_b200/libprmf_b200.so.  Returns the path.  Safe to call from several processes at once: the build runs
+    under a file lock, whoever gets the lock second finds the library fresh, and the library appears
+    atomically (linked to a temporary name, then renamed), so nobody can dlopen a half-written file."""
     if not force and not is_stale():
         return LIB
+    with _build_lock():
+        if not force and not is_stale():         # built by another process while we waited for the lock
+            return LIB
+        return _build_locked(force, verbose)
+
+
+def _build_locked(force, verbose):
     nvcc = nvcc_path()
-    os.makedirs(OBJDIR, exist_ok=True)
     todo = list(SOURCES) if force else (_stale_objects() or [s for s in SOURCES if not os.path.exists(_obj(s))])
 
     def compile_one(src):
@@ -78,11 +102,19 @@ def build_library(force=False, verbose=False):
                 raise RuntimeError("nvcc failed on %s" % src)
             if verbose:
                 sys.stderr.write(res.stdout + res.stderr)
-    link = [nvcc, "-shared"] + ARCH + ["-o", LIB] + [_obj(s) for s in SOURCES] + ["-ldl"]
-    res = subprocess.run(link, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("linking libprmf_b200.so failed")
+    fd, tmp = tempfile.mkstemp(prefix=".libprmf_b200.", suffix=".so.tmp", dir=HERE)
+    os.close(fd)
+    try:
+        link = [nvcc, "-shared"] + ARCH + ["-o", tmp] + [_obj(s) for s in SOURCES] + ["-ldl"]
+        res = subprocess.run(link, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("linking libprmf_b200.so failed")
+        os.chmod(tmp, 0o755)
+        os.replace(tmp, LIB)
+    finally:
+        if os.path.exists(tmp):
+            os.unlink(tmp)
     return LIB
 
 

@@ -1912,40 +1912,76 @@ sum_gram_parts_kernel(const double* __restrict__ G_part, int blocks, int kk2, do
 }
 
 // ----------------------------------------------------------------------------------------------------
-// Factor x pathway tables (restrict :129-194 / score :115-127, force_distinct_lapls :232, find_mins :49)
-// One block per pathway; a warp per factor (strided); lanes over support rows; fixed-order shuffles.
+// Factor x pathway tables (restrict :129-194 / score :115-127, force_distinct_lapls :232, find_mins :49):
+//   mass[c][p]      = sum_{i in supp_p} vu_i^2                      vu = V[:,c] / ||V[:,c]||
+//   quad_norm[c][p] = vu^T (D^-1/2 L_p D^-1/2) vu
+//   quad_raw[c][p]  = V[:,c]^T L_p V[:,c]
+// One block per (pathway, tile of F factors).  The V rows of the support are staged once in shared memory
+// (coalesced row reads: F contiguous factors per gene); thread (row lane, factor) walks the packed CSR row of
+// its support row for its factor, so the CSR of a pathway is read once per factor TILE (the F threads of a row
+// read the same entries: a broadcast) and every neighbour gather is a shared-memory read.  The row lanes of a
+// factor are combined in a fixed order.  Pathways whose support does not fit the staging buffer gather from
+// global memory with the same arithmetic.
 // ----------------------------------------------------------------------------------------------------
+template <int F>
 __global__ void __launch_bounds__(256)
-scores_kernel(const double* __restrict__ V, int k, const double* __restrict__ Gv, Pathways pw,
+scores_kernel(const double* __restrict__ V, int k, const double* __restrict__ Gv, Pathways pw, int smem_rows,
               double* __restrict__ mass, double* __restrict__ quad_norm, double* __restrict__ quad_raw) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    extern __shared__ double sV[];                     // smem_rows x F staged V rows
+    __shared__ double sRed[3][256];
+    constexpr int RL = 256 / F;                        // row lanes
+    const int t = threadIdx.x;
+    const int f = t % F, rl = t / F;
+    const int f0 = (int)blockIdx.y * F;
+    const int c = f0 + f;
+    const bool live = rl < RL && c < k;
+    const double nrm = live ? sqrt(Gv[c * k + c]) : 1.0;
     for (int p = blockIdx.x; p < pw.P; p += gridDim.x) {
         const int64_t beg = pw.path_ptr[p], end = pw.path_ptr[p + 1];
-        for (int c = warp; c < k; c += nw) {
-            const double nrm = sqrt(Gv[c * k + c]);
-            double ms = 0.0, qn = 0.0, qr = 0.0;
-            for (int64_t r = beg + lane; r < end; r += 32) {
-                const double v = V[(int64_t)pw.support_idx[r] * k + c];
+        const int s = (int)(end - beg);
+        const bool staged = s <= smem_rows;
+        __syncthreads();                               // previous pathway's readers are done with sV / sRed
+        if (staged) {
+            for (int idx = t; idx < s * F; idx += 256) {
+                const int r = idx / F, ff = idx - r * F;
+                sV[idx] = (f0 + ff < k) ? V[(int64_t)pw.support_idx[beg + r] * k + f0 + ff] : 0.0;
+            }
+        }
+        __syncthreads();
+        double ms = 0.0, qn = 0.0, qr = 0.0;
+        if (live) {
+            for (int r = rl; r < s; r += RL) {
+                const int64_t gr = beg + r;
+                const double v = staged ? sV[r * F + f] : V[(int64_t)pw.support_idx[gr] * k + c];
                 const double vu = v / nrm;
-                const double ir = pw.isd[r];
-                double yn = (ir * (pw.ldiag[r] * ir)) * vu;
-                double yr = pw.ldiag[r] * v;
-                for (int64_t e2 = pw.row_ptr[r]; e2 < pw.row_ptr[r + 1]; ++e2) {
+                const double ir = pw.isd[gr];
+                const double ld = pw.ldiag[gr];
+                double yn = (ir * (ld * ir)) * vu;
+                double yr = ld * v;
+                const int64_t e1 = pw.row_ptr[gr + 1];
+                for (int64_t e2 = pw.row_ptr[gr]; e2 < e1; ++e2) {
                     const int cl = pw.col_local[e2];
-                    if (beg + cl == r) continue;
-                    const double vc = V[(int64_t)pw.support_idx[beg + cl] * k + c];
-                    yn = fma(ir * (-pw.w[e2] * pw.isd[beg + cl]), vc / nrm, yn);
-                    yr = fma(-pw.w[e2], vc, yr);
+                    if (cl == r) continue;             // a self loop is part of diag(L)
+                    const double vc = staged ? sV[cl * F + f] : V[(int64_t)pw.support_idx[beg + cl] * k + c];
+                    const double we = pw.w[e2];
+                    yn = fma(ir * (-we * pw.isd[beg + cl]), vc / nrm, yn);
+                    yr = fma(-we, vc, yr);
                 }
                 ms = fma(vu, vu, ms);
                 qn = fma(yn, vu, qn);
                 qr = fma(yr, v, qr);
             }
-            ms = warp_sum(ms); qn = warp_sum(qn); qr = warp_sum(qr);
-            if (lane == 0) {
-                mass[(int64_t)c * pw.P + p] = ms;
-                quad_norm[(int64_t)c * pw.P + p] = qn;
-                quad_raw[(int64_t)c * pw.P + p] = qr;
+        }
+        sRed[0][t] = ms; sRed[1][t] = qn; sRed[2][t] = qr;
+        __syncthreads();
+        if (t < 3 * F) {                               // thread (table, factor): the row lanes in order
+            const int tab = t / F, ff = t - tab * F;
+            if (f0 + ff < k) {
+                double a = 0.0;
+#pragma unroll 5
+                for (int l = 0; l < RL; ++l) a += sRed[tab][l * F + ff];
+                double* dst = tab == 0 ? mass : tab == 1 ? quad_norm : quad_raw;
+                dst[(int64_t)(f0 + ff) * pw.P + p] = a;
             }
         }
     }

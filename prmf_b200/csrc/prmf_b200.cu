@@ -95,6 +95,7 @@ struct prmf_handle {
     // pathways
     Pathways pw{};
     int64_t S = 0, E = 0;
+    int64_t max_support = 0;
     std::vector<int64_t> path_ptr_host;
     std::vector<int32_t> support_host;
 
@@ -738,6 +739,30 @@ int launch_objective(prmf_handle* h, double tradeoff, const double* Gu_parts, in
         tradeoff, h->obj, h->step_counter, h->obj_capacity);
     LAUNCH_CHECK("objective_parts_kernel");
     return PRMF_OK;
+}
+
+// k x P score tables of the current V into h->scores_buf (mass | quad_norm | quad_raw)
+template <int F>
+int launch_scores_t(prmf_handle* h) {
+    const int tiles = (h->k + F - 1) / F;
+    // staging buffer: the largest support, capped at 64 KB (larger pathways gather from global memory)
+    const int rows = (int)std::max<int64_t>(1, std::min<int64_t>(h->max_support, (64 * 1024) / (F * 8)));
+    const size_t smem = sizeof(double) * (size_t)rows * F;
+    if (smem > 40 * 1024)
+        CU(cudaFuncSetAttribute(scores_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t cnt = (size_t)h->k * h->pw.P;
+    double* d = h->scores_buf;
+    dim3 grid((unsigned)std::min(h->pw.P, h->sm_count * 16), (unsigned)tiles);
+    scores_kernel<F><<<grid, 256, smem, h->stream>>>(h->Vbuf[h->vcur], h->k, h->Gv, h->pw, rows, d, d + cnt, d + 2 * cnt);
+    LAUNCH_CHECK("scores_kernel");
+    return PRMF_OK;
+}
+
+int launch_scores(prmf_handle* h) {
+    if (h->k <= 4) return launch_scores_t<4>(h);
+    if (h->k <= 8) return launch_scores_t<8>(h);
+    if (h->k <= 10) return launch_scores_t<10>(h);
+    return launch_scores_t<16>(h);
 }
 
 const double* cur_U(const prmf_handle* h) { return h->ahead == 2 ? h->U2 : h->U; }
@@ -1498,6 +1523,8 @@ int prmf_set_pathways(prmf_handle* h, int32_t P, const int64_t* path_ptr, const 
     h->scores_buf = h->pw_arena.take<double>((size_t)3 * h->k * P);
     if (!h->scores_buf) return fail(h, PRMF_ERR_NOMEM, "pathway arena exhausted (scores)");
     h->pw = pw; h->S = S; h->E = E;
+    h->max_support = 0;
+    for (int32_t p = 0; p < P; ++p) h->max_support = std::max(h->max_support, path_ptr[p + 1] - path_ptr[p]);
     h->path_ptr_host.assign(path_ptr, path_ptr + P + 1);
     h->row_ptr_host.assign(row_ptr, row_ptr + S + 1);
     h->have_pw = true;
@@ -1572,9 +1599,8 @@ int prmf_scores(prmf_handle* h, double* mass, double* quad_norm, double* quad_ra
     CU(cudaSetDevice(h->device));
     const size_t cnt = (size_t)h->k * h->pw.P;
     double* d = h->scores_buf;
-    scores_kernel<<<std::min(h->pw.P, h->sm_count * 8), 256, 0, h->stream>>>(h->Vbuf[h->vcur], h->k, h->Gv, h->pw, d,
-                                                                             d + cnt, d + 2 * cnt);
-    LAUNCH_CHECK("scores_kernel");
+    int rc_s = launch_scores(h);
+    if (rc_s) return rc_s;
     if (mass) CU(cudaMemcpyAsync(mass, d, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (quad_norm) CU(cudaMemcpyAsync(quad_norm, d + cnt, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (quad_raw) CU(cudaMemcpyAsync(quad_raw, d + 2 * cnt, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1591,9 +1617,8 @@ int prmf_block_end(prmf_handle* h, int n_steps, double* obj_parts, double* gamma
         if (!h->have_pw || !h->have_UV) return fail(h, PRMF_ERR_STATE, "prmf_block_end needs pathways and V for the scores");
         const size_t cnt = (size_t)h->k * h->pw.P;
         double* d = h->scores_buf;
-        scores_kernel<<<std::min(h->pw.P, h->sm_count * 8), 256, 0, h->stream>>>(h->Vbuf[h->vcur], h->k, h->Gv, h->pw, d,
-                                                                                 d + cnt, d + 2 * cnt);
-        LAUNCH_CHECK("scores_kernel");
+        int rc_s = launch_scores(h);
+        if (rc_s) return rc_s;
         if (mass) CU(cudaMemcpyAsync(mass, d, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         if (quad_norm) CU(cudaMemcpyAsync(quad_norm, d + cnt, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         if (quad_raw) CU(cudaMemcpyAsync(quad_raw, d + 2 * cnt, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

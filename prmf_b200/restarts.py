@@ -97,6 +97,8 @@ def main(argv=None):
         sys.exit(26)
     cmds = build_commands(args)
     gpus = visible_gpus(args.gpus)
+    from . import _lib
+    _lib.load()                                                   # build once, before the workers fan out
     for run_outdir, _ in cmds:
         os.mkdir(run_outdir)                                      # as the reference: fails if it exists
     running, results, todo = {}, {}, list(enumerate(cmds))

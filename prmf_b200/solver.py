@@ -458,8 +458,10 @@ def nmf_pathway(X, Gs, gamma=1.0, delta=1.0, tradeoff=None, k_latent=6, tol=1e-3
             eng.restore_best()
             obj_data = best_obj_data
         U_local, V = eng.get_UV()
-    finally:
         ctx.barrier()          # peers may still be reading this rank's exchange buffer
+    finally:
+        # (no barrier on the error path: a failed rank must surface its exception instead of parking in a
+        #  collective while its peers wait for it inside a kernel; their bounded device waits then fail too)
         eng.close()
     U = ctx.all_gather_rows(U_local, m)
     obj_data = dict(obj_data)

@@ -624,6 +624,7 @@ def run_ours(a):
                 "" if a.gpus == 1 else (", per-step sum over ranks of [X^T U | U^T U]: " + {
                     "nccl": "ncclAllReduce", "p2p-v-update": "NVLink peer loads fused into the V-update kernel",
                     "p2p-pass2": "NVLink peer exchange fused into the pass-2 X-stream kernel (exchange + V update)",
+                    "p2p-push-block": "NVLink peer stores (push) inside the persistent step kernel, summed in rank order from local memory",
                     "none": "none"}.get(exch_mode, exch_mode))),
             "inner_steps_per_s": 1000.0 / inner_ms,
             "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "time_to_converge": ttc,

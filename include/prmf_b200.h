@@ -34,6 +34,7 @@ typedef struct prmf_handle prmf_handle;
 #define PRMF_ERR_STATE      -3
 #define PRMF_ERR_NCCL       -4
 #define PRMF_ERR_NOMEM      -5
+#define PRMF_ERR_TIMEOUT    -6   /* a bounded device-side wait expired (lost launch, dead peer rank); the handle refuses further steps */
 
 #define PRMF_OBJ_STRIDE      8   /* doubles per inner step written by prmf_step (see below) */
 #define PRMF_UNIQUE_ID_BYTES 128
@@ -166,7 +167,8 @@ int prmf_p2p_attach(prmf_handle* h, int rank, int nranks, const uint8_t* handles
 int prmf_p2p_finalize(prmf_handle* h);
 
 /* How the per-step sum over ranks is done: 0 one rank, 1 ncclAllReduce, 2 NVLink peer loads inside the V-update
- * kernel, 3 NVLink peer loads inside the pass-2 X-stream kernel (prmf_p2p_finalize). */
+ * kernel, 3 NVLink peer loads inside the pass-2 X-stream kernel, 4 NVLink peer stores (push) inside the persistent
+ * step kernel (the default for k <= 10 when every rank can take it; agreed in prmf_p2p_finalize). */
 int prmf_exchange_mode(const prmf_handle* h);
 
 /* ---- introspection used by bench.py and the tests ---------------------------------------------------*/
@@ -179,6 +181,11 @@ int64_t prmf_launch_count(const prmf_handle* h);
 int prmf_kernel_times(prmf_handle* h, int reset, double* phase_ms, int64_t* phase_count);
 /* Enable (1) / disable (0) per-kernel event timing inside prmf_step (off by default). */
 int prmf_set_profiling(prmf_handle* h, int on);
+/* Fault injection for the tests of the bounded device waits (a lost launch or a dead peer must come
+ * back as an error code, not as a hang).  kind 1: the next persistent step launch waits for a thread-block arrival
+ * that never happens; kind 2: it waits for a peer-exchange flag that never comes.  The waits expire after
+ * PRMF_SPIN_TIMEOUT_MS (environment, default 10 000 ms) and the step returns PRMF_ERR_TIMEOUT. */
+int prmf_debug_inject_fault(prmf_handle* h, int kind);
 /* The cudaStream_t the handle launches on. */
 void* prmf_stream(const prmf_handle* h);
 

@@ -1925,9 +1925,16 @@ sum_gram_parts_kernel(const double* __restrict__ G_part, int blocks, int kk2, do
 // ----------------------------------------------------------------------------------------------------
 template <int F>
 __global__ void __launch_bounds__(256)
-scores_kernel(const double* __restrict__ V, int k, const double* __restrict__ Gv, Pathways pw, int smem_rows,
+scores_kernel(const double* __restrict__ V, int k, const double* __restrict__ Gv, Pathways pw, int rows_cap, int edges_cap,
               double* __restrict__ mass, double* __restrict__ quad_norm, double* __restrict__ quad_raw) {
-    extern __shared__ double sV[];                     // smem_rows x F staged V rows
+    // staged copy of one pathway: V rows of the support (F factors), isd, ldiag, w | row offsets, neighbour indices
+    extern __shared__ double s_dyn[];
+    double* sV = s_dyn;                                // rows_cap x F
+    double* sIsd = sV + (size_t)rows_cap * F;          // rows_cap
+    double* sLd = sIsd + rows_cap;                     // rows_cap
+    double* sW = sLd + rows_cap;                       // edges_cap
+    int32_t* sRow = reinterpret_cast<int32_t*>(sW + edges_cap);   // rows_cap + 1 (relative to the pathway's first edge)
+    int32_t* sCol = sRow + rows_cap + 1;               // edges_cap
     __shared__ double sRed[3][256];
     constexpr int RL = 256 / F;                        // row lanes
     const int t = threadIdx.x;
@@ -1939,20 +1946,46 @@ scores_kernel(const double* __restrict__ V, int k, const double* __restrict__ Gv
     for (int p = blockIdx.x; p < pw.P; p += gridDim.x) {
         const int64_t beg = pw.path_ptr[p], end = pw.path_ptr[p + 1];
         const int s = (int)(end - beg);
-        const bool staged = s <= smem_rows;
-        __syncthreads();                               // previous pathway's readers are done with sV / sRed
-        if (staged) {
+        const int64_t ebeg = pw.row_ptr[beg];
+        const int ne = (int)(pw.row_ptr[end] - ebeg);
+        const bool staged = s <= rows_cap && ne <= edges_cap;
+        __syncthreads();                               // previous pathway's readers are done with the staged copy / sRed
+        if (staged) {                                  // every range is contiguous in the packed tables: coalesced copies
             for (int idx = t; idx < s * F; idx += 256) {
                 const int r = idx / F, ff = idx - r * F;
                 sV[idx] = (f0 + ff < k) ? V[(int64_t)pw.support_idx[beg + r] * k + f0 + ff] : 0.0;
             }
+            for (int r = t; r < s; r += 256) { sIsd[r] = pw.isd[beg + r]; sLd[r] = pw.ldiag[beg + r]; }
+            for (int r = t; r <= s; r += 256) sRow[r] = (int32_t)(pw.row_ptr[beg + r] - ebeg);
+            for (int e = t; e < ne; e += 256) { sCol[e] = pw.col_local[ebeg + e]; sW[e] = pw.w[ebeg + e]; }
         }
         __syncthreads();
         double ms = 0.0, qn = 0.0, qr = 0.0;
-        if (live) {
+        if (live && staged) {
+            for (int r = rl; r < s; r += RL) {
+                const double v = sV[r * F + f];
+                const double vu = v / nrm;
+                const double ir = sIsd[r];
+                const double ld = sLd[r];
+                double yn = (ir * (ld * ir)) * vu;
+                double yr = ld * v;
+                const int e1 = sRow[r + 1];
+                for (int e2 = sRow[r]; e2 < e1; ++e2) {
+                    const int cl = sCol[e2];
+                    if (cl == r) continue;             // a self loop is part of diag(L)
+                    const double vc = sV[cl * F + f];
+                    const double we = sW[e2];
+                    yn = fma(ir * (-we * sIsd[cl]), vc / nrm, yn);
+                    yr = fma(-we, vc, yr);
+                }
+                ms = fma(vu, vu, ms);
+                qn = fma(yn, vu, qn);
+                qr = fma(yr, v, qr);
+            }
+        } else if (live) {                             // support or edge list larger than the staging buffers
             for (int r = rl; r < s; r += RL) {
                 const int64_t gr = beg + r;
-                const double v = staged ? sV[r * F + f] : V[(int64_t)pw.support_idx[gr] * k + c];
+                const double v = V[(int64_t)pw.support_idx[gr] * k + c];
                 const double vu = v / nrm;
                 const double ir = pw.isd[gr];
                 const double ld = pw.ldiag[gr];
@@ -1961,8 +1994,8 @@ scores_kernel(const double* __restrict__ V, int k, const double* __restrict__ Gv
                 const int64_t e1 = pw.row_ptr[gr + 1];
                 for (int64_t e2 = pw.row_ptr[gr]; e2 < e1; ++e2) {
                     const int cl = pw.col_local[e2];
-                    if (cl == r) continue;             // a self loop is part of diag(L)
-                    const double vc = staged ? sV[cl * F + f] : V[(int64_t)pw.support_idx[beg + cl] * k + c];
+                    if (cl == r) continue;
+                    const double vc = V[(int64_t)pw.support_idx[beg + cl] * k + c];
                     const double we = pw.w[e2];
                     yn = fma(ir * (-we * pw.isd[beg + cl]), vc / nrm, yn);
                     yr = fma(-we, vc, yr);

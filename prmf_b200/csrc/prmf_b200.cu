@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "block.cuh"
 #include "fused.cuh"
 #include "tf32.cuh"
 #include "nccl_dyn.h"
@@ -95,7 +96,7 @@ struct prmf_handle {
     // pathways
     Pathways pw{};
     int64_t S = 0, E = 0;
-    int64_t max_support = 0;
+    int64_t max_support = 0, max_edges = 0;
     std::vector<int64_t> path_ptr_host;
     std::vector<int32_t> support_host;
 
@@ -130,8 +131,22 @@ struct prmf_handle {
     double* hist = nullptr;
     double *hist_Gu = nullptr, *hist_Gvp = nullptr, *hist_VBp = nullptr, *hist_vh = nullptr;
     bool defer_ok = false;
-    bool epi_coop = true;                     // cooperative launch (co-residency guaranteed by the driver)
     double *epi_part2 = nullptr, *epi_vb2 = nullptr;
+
+    // persistent step kernel (block.cuh): a whole block of inner steps per cooperative launch
+    bool use_block = false;                   // this rank can take it (fused-tail geometry, deferred objective, smem fits)
+    bool blk_xchg = false;                    // sharded: every rank takes it with the same geometry (prmf_p2p_finalize)
+    unsigned long long* blk_ctr = nullptr;    // arrive1 | done1 | arrive2 | done2 | udone | vdone
+    unsigned long long blk_n1 = 0, blk_n2 = 0, blk_xseq = 0;
+    size_t blk_smem = 0;
+    uint32_t blk_stage_bytes = 0;
+    unsigned int* err_word = nullptr;         // device: set by a bounded wait that expired
+    unsigned int* err_host = nullptr;         // pinned host copy read at the end of every block
+    unsigned long long spin_timeout_ns = 10000000000ull;
+    bool failed = false;                      // a launch failed or a device wait expired: no further steps
+    double* xbuf = nullptr;                   // push-exchange receive buffer inside p2p_buf
+    unsigned long long* xflag = nullptr;
+    size_t xcount = 0;
 
     // single-pass fused X kernel (opt-in: PRMF_FUSED=1)
     bool use_fused = false;
@@ -304,10 +319,8 @@ int launch_skinny_epi_t(prmf_handle* h, int epi, const double* M, int64_t ldm, i
         default: return fail(h, PRMF_ERR_STATE, "bad fused-tail id %d", epi);
     }
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (h->epi_coop)
-        CU(cudaLaunchCooperativeKernel(fn, grid, dim3(kTmaThreads), args, smem, h->stream));
-    else
-        CU(cudaLaunchKernel(fn, grid, dim3(kTmaThreads), args, smem, h->stream));
+    // always cooperative: the CTAs of a panel wait for each other, so co-residency must be guaranteed by the driver
+    CU(cudaLaunchCooperativeKernel(fn, grid, dim3(kTmaThreads), args, smem, h->stream));
     return PRMF_OK;
 }
 
@@ -745,15 +758,24 @@ int launch_objective(prmf_handle* h, double tradeoff, const double* Gu_parts, in
 template <int F>
 int launch_scores_t(prmf_handle* h) {
     const int tiles = (h->k + F - 1) / F;
-    // staging buffer: the largest support, capped at 64 KB (larger pathways gather from global memory)
-    const int rows = (int)std::max<int64_t>(1, std::min<int64_t>(h->max_support, (64 * 1024) / (F * 8)));
-    const size_t smem = sizeof(double) * (size_t)rows * F;
+    // staging buffers sized for the largest pathway, capped near 96 KB (larger pathways gather from global memory)
+    int rows = (int)std::max<int64_t>(1, std::min<int64_t>(h->max_support, 2048));
+    int edges = (int)std::max<int64_t>(1, std::min<int64_t>(h->max_edges, 16384));
+    auto bytes = [&](int r, int e) {
+        return sizeof(double) * ((size_t)r * (F + 2) + e) + sizeof(int32_t) * ((size_t)r + 1 + e + 1);
+    };
+    while (bytes(rows, edges) > 96 * 1024 && (rows > 64 || edges > 256)) {
+        if (rows > 64) rows = rows * 3 / 4;
+        if (edges > 256) edges = edges * 3 / 4;
+    }
+    edges = (edges + 1) & ~1;                       // keeps the int32 arrays 8-byte aligned behind the doubles
+    const size_t smem = bytes(rows, edges);
     if (smem > 40 * 1024)
         CU(cudaFuncSetAttribute(scores_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t cnt = (size_t)h->k * h->pw.P;
     double* d = h->scores_buf;
     dim3 grid((unsigned)std::min(h->pw.P, h->sm_count * 16), (unsigned)tiles);
-    scores_kernel<F><<<grid, 256, smem, h->stream>>>(h->Vbuf[h->vcur], h->k, h->Gv, h->pw, rows, d, d + cnt, d + 2 * cnt);
+    scores_kernel<F><<<grid, 256, smem, h->stream>>>(h->Vbuf[h->vcur], h->k, h->Gv, h->pw, rows, edges, d, d + cnt, d + 2 * cnt);
     LAUNCH_CHECK("scores_kernel");
     return PRMF_OK;
 }
@@ -763,6 +785,73 @@ int launch_scores(prmf_handle* h) {
     if (h->k <= 8) return launch_scores_t<8>(h);
     if (h->k <= 10) return launch_scores_t<10>(h);
     return launch_scores_t<16>(h);
+}
+
+// persistent step kernel: halves [h0, h0 + nh) of a block in one cooperative launch (block.cuh)
+template <int K>
+int launch_block_t(prmf_handle* h, const BlockParams& prm, int grid) {
+    CU(cudaFuncSetAttribute(block_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->blk_smem));
+    BlockParams copy = prm;
+    void* args[] = {(void*)&copy};
+    CU(cudaLaunchCooperativeKernel((const void*)block_kernel<K>, dim3((unsigned)grid), dim3(kTmaThreads), args, h->blk_smem,
+                                   h->stream));
+    return PRMF_OK;
+}
+
+bool block_path(const prmf_handle* h) { return h->use_block && (h->comm == nullptr || h->blk_xchg); }
+
+int launch_block(prmf_handle* h, int h0, int nh) {
+    if (nh <= 0) return PRMF_OK;
+    BlockParams prm{};
+    prm.X = h->X; prm.Xt = h->Xt; prm.ldx = h->ldx; prm.ldxt = h->ldxt; prm.m = h->m; prm.n = h->n;
+    prm.panels1 = h->tpanels1; prm.panel_w1 = h->tpanel_w1; prm.chunks1 = h->tchunks1; prm.rpc1 = h->trows_per_chunk1;
+    prm.panels2 = h->tpanels; prm.panel_w2 = h->tpanel_w; prm.chunks2 = h->tchunks; prm.rpc2 = h->trows_per_chunk;
+    prm.stages = h->tma_stages;
+    prm.ring_stage_bytes = h->blk_stage_bytes;
+    prm.U[0] = h->U; prm.U[1] = h->U2;
+    prm.V[0] = h->Vbuf[h->vcur]; prm.V[1] = h->Vbuf[h->vcur ^ 1];
+    prm.Apart = h->Apart; prm.Bpart = h->Bpart; prm.Gu_part = h->Gu_part;
+    prm.part2 = h->epi_part2; prm.vb2 = h->epi_vb2;
+    prm.Gv0 = h->Gv;
+    unsigned long long* c = h->blk_ctr;
+    prm.arrive1 = c; c += h->tpanels1;
+    prm.done1 = c; c += h->tpanels1;
+    prm.arrive2 = c; c += h->tpanels;
+    prm.done2 = c; c += h->tpanels;
+    prm.udone = c; prm.vdone = c + 1;
+    prm.base1 = h->blk_n1; prm.base2 = h->blk_n2;
+    prm.h0 = h0; prm.nh = nh;
+    prm.pw = h->pw; prm.active = h->active; prm.pos = h->pos; prm.gd = h->gd;
+    prm.hist_Gu = h->hist_Gu; prm.hist_Gvp = h->hist_Gvp; prm.hist_VBp = h->hist_VBp; prm.hist_vh = h->hist_vh;
+    prm.doff = h->as_off;
+    prm.err = h->err_word; prm.timeout_ns = h->spin_timeout_ns;
+    prm.nranks = h->comm ? h->nranks : 1; prm.rank = h->rank;
+    if (prm.nranks > 1) {
+        const size_t off_buf = (size_t)(h->xbuf - h->p2p_buf);                 // same layout in every rank's buffer
+        const size_t off_flag = (size_t)((double*)h->xflag - h->p2p_buf);
+        for (int r = 0; r < h->nranks; ++r) {
+            prm.xbuf[r] = (double*)h->peer_base[r] + off_buf;
+            prm.xflag[r] = (unsigned long long*)((double*)h->peer_base[r] + off_flag);
+        }
+        prm.xcount = h->xcount;
+        prm.xbase = h->blk_xseq;
+    }
+    int n_p1 = 0, n_p2 = 0;
+    for (int i = 0; i < nh; ++i) (((h0 + i) & 1) == 0 ? n_p1 : n_p2)++;
+    const int grid = std::max(h->tpanels1 * h->tchunks1, h->tpanels * h->tchunks);
+    int rc = 0;
+    KT_SWITCH_RC(h->k, rc, launch_block_t, h, prm, grid);
+    if (!rc) {
+        h->launches++;
+        cudaError_t e_ = cudaGetLastError();
+        if (e_ != cudaSuccess) rc = fail(h, PRMF_ERR_CUDA, "launch of block_kernel failed: %s", cudaGetErrorString(e_));
+    }
+    if (rc) { h->failed = true; return rc; }      // the counters below only move for a launch that is really queued
+    h->blk_n1 += n_p1; h->blk_n2 += n_p2;
+    if (prm.nranks > 1) h->blk_xseq += n_p2;
+    if (n_p1 & 1) std::swap(h->U, h->U2);
+    if (n_p2 & 1) h->vcur ^= 1;
+    return PRMF_OK;
 }
 
 const double* cur_U(const prmf_handle* h) { return h->ahead == 2 ? h->U2 : h->U; }
@@ -776,7 +865,11 @@ int prefetch_pass1(prmf_handle* h) {
     if (h->ahead || h->profiling || h->use_fused || h->m == 0) return PRMF_OK;
     if (!h->have_X || !h->have_UV) return PRMF_OK;
     int rc = 0;
-    if (h->use_epi) {
+    if (h->failed) return PRMF_OK;
+    if (block_path(h)) {
+        if ((rc = launch_block(h, 0, 1))) return rc;        // pass 1 + U update of the next block's first step
+        h->ahead = 2;
+    } else if (h->use_epi) {
         if ((rc = launch_xv_epi(h))) return rc;
         h->ahead = 2;
     } else {
@@ -824,6 +917,7 @@ int enqueue_steps(prmf_handle* h, int n_steps, double gamma, double delta, doubl
     if (!h->have_X || !h->have_UV || !h->have_pw || !h->have_active)
         return fail(h, PRMF_ERR_STATE, "prmf_step needs X, U/V, pathways and the active set first");
     if (n_steps <= 0) return fail(h, PRMF_ERR_ARG, "n_steps must be positive");
+    if (h->failed) return fail(h, PRMF_ERR_STATE, "the handle is in a failed state (an earlier launch failed or a device wait expired)");
     CU(cudaSetDevice(h->device));
     int rc = ensure_obj_capacity(h, n_steps);
     if (rc) return rc;
@@ -848,8 +942,19 @@ int enqueue_steps(prmf_handle* h, int n_steps, double gamma, double delta, doubl
         cudaEventRecord(h->ev_pool[h->ev_pairs.back().second + 1], h->stream);
     };
     // deferred objective: one GPU, or sharded with the in-kernel exchange (every rank evaluates the same numbers)
-    const bool defer = h->defer_ok && h->use_epi && (h->comm == nullptr || h->use_xchg) && tradeoff < 0.0 &&
+    const bool defer = h->defer_ok && h->use_epi && (h->comm == nullptr || h->use_xchg || h->blk_xchg) && tradeoff < 0.0 &&
                        !h->profiling && h->as.n_diag <= kVhCap;
+    if (defer && block_path(h)) {
+        // the whole block in ONE persistent launch (block.cuh) + the deferred objective
+        const int h0 = h->ahead != 0 ? 1 : 0;               // pass 1 + U update of step 0 already done by prmf_block_end
+        h->ahead = 0;
+        if ((rc = launch_block(h, h0, 2 * n_steps - h0))) return rc;
+        objective_deferred_kernel<<<n_steps, kTailThreads, obj_smem(h), h->stream>>>(
+            h->k, h->hist_Gu, h->hist_Gvp, h->hist_VBp, h->tpanels, h->hist_vh, kVhCap, h->normX_sq, h->as, h->Gv,
+            h->gd, h->obj, h->obj_capacity);
+        LAUNCH_CHECK("objective_deferred_kernel");
+        return PRMF_OK;
+    }
     for (int s = 0; s < n_steps; ++s) {
         const bool skip_pass1 = s == 0 && h->ahead != 0;      // already enqueued by prmf_block_end
         if (skip_pass1) h->ahead = 0;
@@ -924,6 +1029,14 @@ int enqueue_steps(prmf_handle* h, int n_steps, double gamma, double delta, doubl
     return PRMF_OK;
 }
 
+int check_err_word(prmf_handle* h, unsigned int errw) {
+    if (errw == 0) return PRMF_OK;
+    h->failed = true;
+    return fail(h, PRMF_ERR_TIMEOUT, "a device-side wait expired after %.1f s (%s%s); results of this block are invalid",
+                h->spin_timeout_ns * 1e-9, (errw & kErrTimeoutLocal) ? "waiting for another thread block of this GPU " : "",
+                (errw & kErrTimeoutPeer) ? "waiting for a peer rank's exchange flag" : "");
+}
+
 int collect(prmf_handle* h, int n_steps, double* obj_parts, double* gamma_delta_out) {
     CU(cudaSetDevice(h->device));
     if (n_steps > h->obj_capacity) return fail(h, PRMF_ERR_ARG, "collect: more steps than were run");
@@ -931,9 +1044,11 @@ int collect(prmf_handle* h, int n_steps, double* obj_parts, double* gamma_delta_
         CU(cudaMemcpyAsync(obj_parts, h->obj, sizeof(double) * n_steps * kObjStride, cudaMemcpyDeviceToHost, h->stream));
     if (gamma_delta_out)
         CU(cudaMemcpyAsync(gamma_delta_out, h->gd, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    unsigned int errw = 0;
+    CU(cudaMemcpyAsync(&errw, h->err_word, sizeof errw, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     if (h->profiling) harvest_events(h);
-    return PRMF_OK;
+    return check_err_word(h, errw);
 }
 
 // ---- TF32 mode set-up ---------------------------------------------------------------------------------
@@ -1231,8 +1346,6 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
         const char* ee = getenv("PRMF_EPI");
         h->use_epi = !(ee && atoi(ee) == 0) && h->use_tma && k <= 10 && h->tma_rs == 8 && m_local > 0 && !h->x_tf32 &&
                      !h->use_fused && h->tpanels1 * h->tchunks1 <= h->sm_count && h->tpanels * h->tchunks <= h->sm_count;
-        const char* ec = getenv("PRMF_COOP");
-        h->epi_coop = !(ec && atoi(ec) == 0);
         if (h->use_epi) {
             // the last CTA of a panel reuses the ring for Gv/Gu, the slice sums and the panel's new rows
             const size_t share1 = (size_t)(h->tpanel_w1 + h->tchunks1 - 1) / h->tchunks1 * k;
@@ -1263,6 +1376,7 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
         total += pad(128, d) + 4 * pad(kk2, d) + pad((size_t)gu_parts_max * kk2, d) + pad((size_t)gv_parts_max * kk2, d);
         total += pad(gv_parts_max, d) + pad((size_t)std::max({h->chunks, h->tchunks, h->fp.groups, h->tc_chunks2}) * nk, d);   // VB_part, Bpart
         total += pad(2 * ((size_t)h->tpanels1 + h->tpanels) + 2, sizeof(unsigned long long));     // fused-tail counters
+        total += pad(2 * ((size_t)h->tpanels1 + h->tpanels) + 2, sizeof(unsigned long long)) + pad(1, sizeof(unsigned int));   // block kernel
         total += pad((size_t)std::max(h->tpanels1 * h->tchunks1, h->tpanels * h->tchunks) * kk2, d) +
                  pad((size_t)h->tpanels * h->tchunks, d);                                          // per-CTA partials
         total += pad((size_t)nk + kk2 + 2, d) + pad(1, d) + pad((size_t)h->sm_count * 8, d) + pad(2, d);
@@ -1296,6 +1410,8 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
     TAKE(h->Gv_part, double, (size_t)gv_parts_max * kk2);
     TAKE(h->VB_part, double, gv_parts_max);
     TAKE(h->epi_counters, unsigned long long, 2 * ((size_t)h->tpanels1 + h->tpanels) + 2);
+    TAKE(h->blk_ctr, unsigned long long, 2 * ((size_t)h->tpanels1 + h->tpanels) + 2);
+    TAKE(h->err_word, unsigned int, 1);
     TAKE(h->epi_part2, double, (size_t)std::max(h->tpanels1 * h->tchunks1, h->tpanels * h->tchunks) * kk2);
     TAKE(h->epi_vb2, double, (size_t)h->tpanels * h->tchunks);
     TAKE(h->Bpart, double, (size_t)std::max({h->chunks, h->tchunks, h->fp.groups, h->tc_chunks2}) * nk);
@@ -1320,6 +1436,8 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
         if (h->Xt) cudaMemsetAsync(h->Xt, 0, sizeof(double) * n * h->ldxt, h->stream);
         cudaMemsetAsync(h->ticket, 0, sizeof(unsigned int), h->stream);
         cudaMemsetAsync(h->epi_counters, 0, sizeof(unsigned long long) * (2 * ((size_t)h->tpanels1 + h->tpanels) + 2), h->stream);
+        cudaMemsetAsync(h->blk_ctr, 0, sizeof(unsigned long long) * (2 * ((size_t)h->tpanels1 + h->tpanels) + 2), h->stream);
+        cudaMemsetAsync(h->err_word, 0, sizeof(unsigned int), h->stream);
         cudaMemsetAsync(h->U, 0, sizeof(double) * (m_local + pad_rows) * k, h->stream);
         cudaMemsetAsync(h->U2, 0, sizeof(double) * (m_local + pad_rows) * k, h->stream);
         if (h->use_fused) {
@@ -1347,6 +1465,20 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
                 h->defer_ok = true;
             }
         }
+    }
+    if (!rc) {
+        // persistent step kernel: needs the fused-tail geometry, the per-step history of the deferred objective, and
+        // ring + tail scratch within the shared memory of one CTA
+        const char* eb = getenv("PRMF_BLOCK");
+        const char* et = getenv("PRMF_SPIN_TIMEOUT_MS");
+        if (et && atof(et) > 0) h->spin_timeout_ns = (unsigned long long)(atof(et) * 1e6);
+        const size_t wb = ((size_t)kBlkRS * k * 8 + 127) & ~(size_t)127;
+        h->blk_stage_bytes = (uint32_t)((size_t)kBlkRS * std::max(h->tpanel_w1, h->tpanel_w) * 8 + wb);
+        h->blk_smem = (size_t)h->tma_stages * h->blk_stage_bytes + 2 * h->tma_stages * sizeof(uint64_t) +
+                      sizeof(double) * (128 + 8 * (size_t)k * k + 3 * (size_t)kBlkTile * k);
+        h->use_block = h->use_epi && h->defer_ok && !(eb && atoi(eb) == 0) && h->blk_smem <= 227 * 1024;
+        if (cudaHostAlloc((void**)&h->err_host, sizeof(unsigned int), cudaHostAllocDefault) == cudaSuccess) *h->err_host = 0;
+        else h->err_host = nullptr;
     }
     // opt in to large dynamic shared memory where k needs it
     if (!rc && h->big_k) {
@@ -1385,6 +1517,7 @@ int prmf_destroy(prmf_handle* h) {
         for (int r = 0; r < h->nranks; ++r)
             if (r != h->rank && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
     if (h->ev_sync) cudaEventDestroy(h->ev_sync);
+    if (h->err_host) cudaFreeHost(h->err_host);
     if (h->p2p_buf) cudaFree(h->p2p_buf);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->X) cudaFree(h->X);
@@ -1524,7 +1657,11 @@ int prmf_set_pathways(prmf_handle* h, int32_t P, const int64_t* path_ptr, const 
     if (!h->scores_buf) return fail(h, PRMF_ERR_NOMEM, "pathway arena exhausted (scores)");
     h->pw = pw; h->S = S; h->E = E;
     h->max_support = 0;
-    for (int32_t p = 0; p < P; ++p) h->max_support = std::max(h->max_support, path_ptr[p + 1] - path_ptr[p]);
+    h->max_edges = 0;
+    for (int32_t p = 0; p < P; ++p) {
+        h->max_support = std::max(h->max_support, path_ptr[p + 1] - path_ptr[p]);
+        h->max_edges = std::max(h->max_edges, row_ptr[path_ptr[p + 1]] - row_ptr[path_ptr[p]]);
+    }
     h->path_ptr_host.assign(path_ptr, path_ptr + P + 1);
     h->row_ptr_host.assign(row_ptr, row_ptr + S + 1);
     h->have_pw = true;
@@ -1627,6 +1764,7 @@ int prmf_block_end(prmf_handle* h, int n_steps, double* obj_parts, double* gamma
         CU(cudaMemcpyAsync(obj_parts, h->obj, sizeof(double) * n_steps * kObjStride, cudaMemcpyDeviceToHost, h->stream));
     if (gamma_delta_out)
         CU(cudaMemcpyAsync(gamma_delta_out, h->gd, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (h->err_host) CU(cudaMemcpyAsync(h->err_host, h->err_word, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
     if (!h->ev_sync) CU(cudaEventCreateWithFlags(&h->ev_sync, cudaEventDisableTiming));
     CU(cudaEventRecord(h->ev_sync, h->stream));
     if (prefetch) {
@@ -1638,7 +1776,7 @@ int prmf_block_end(prmf_handle* h, int n_steps, double* obj_parts, double* gamma
         CU(cudaStreamSynchronize(h->stream));
         harvest_events(h);
     }
-    return PRMF_OK;
+    return check_err_word(h, h->err_host ? *h->err_host : 0u);
 }
 
 int prmf_snapshot_best(prmf_handle* h) {
@@ -1772,10 +1910,17 @@ int prmf_p2p_export(prmf_handle* h, uint8_t* handle_out) {
     CU(cudaSetDevice(h->device));
     if (!h->p2p_buf) {
         h->p2p_red_count = (size_t)round_up(h->n * h->k + (int64_t)h->k * h->k + 2, 32);
-        const size_t total = 2 * h->p2p_red_count + 64 + (size_t)kMaxPeers * (h->sm_count + 2);   // + per-CTA flags
+        const size_t old_total = 2 * h->p2p_red_count + 64 + (size_t)kMaxPeers * (h->sm_count + 2);   // + per-CTA flags
+        // push exchange of the persistent step kernel: receive slots [parity][source rank][n*k + k*k] + its flags
+        h->xcount = h->p2p_red_count;
+        const size_t xdoubles = 2 * (size_t)kMaxPeers * h->xcount;
+        const size_t xflags = (size_t)kMaxPeers * (h->sm_count + 2);
+        const size_t total = old_total + xdoubles + xflags;
         int rc = dalloc(h, &h->p2p_buf, total);
         if (rc) return rc;
         CU(cudaMemset(h->p2p_buf, 0, total * sizeof(double)));
+        h->xbuf = h->p2p_buf + old_total;
+        h->xflag = (unsigned long long*)(h->xbuf + xdoubles);
     }
     cudaIpcMemHandle_t hd;
     CU(cudaIpcGetMemHandle(&hd, h->p2p_buf));
@@ -1815,20 +1960,26 @@ int prmf_p2p_finalize(prmf_handle* h) {
     // on flags nobody writes)
     // opt-in (PRMF_XCHG=1): measured at 2 GPUs it does not beat the exchange inside the V-update kernel yet
     const char* ex = getenv("PRMF_XCHG");
-    const double mine = (h->use_epi && ex && atoi(ex) == 1) ? 1.0 : 0.0;
-    CU(cudaMemcpyAsync(h->scal_part, &mine, sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    int rc = allreduce(h, h->scal_part, 1);
+    // [in-kernel pull exchange wanted | persistent step kernel possible | pass-2 chunks | chunks^2]: the push exchange of
+    // the persistent kernel pairs CTA c of every rank, so all ranks must split the genes the same way
+    const double mine[4] = {(h->use_epi && ex && atoi(ex) == 1) ? 1.0 : 0.0, h->use_block ? 1.0 : 0.0, (double)h->tchunks,
+                            (double)h->tchunks * h->tchunks};
+    CU(cudaMemcpyAsync(h->scal_part, mine, sizeof mine, cudaMemcpyHostToDevice, h->stream));
+    int rc = allreduce(h, h->scal_part, 4);
     if (rc) return rc;
-    double sum = 0.0;
-    CU(cudaMemcpyAsync(&sum, h->scal_part, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    double sum[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(sum, h->scal_part, sizeof sum, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    h->use_xchg = sum > h->nranks - 0.5;
+    h->use_xchg = sum[0] > h->nranks - 0.5;
+    const bool same_chunks = std::fabs(h->nranks * sum[3] - sum[2] * sum[2]) < 0.5;
+    h->blk_xchg = !h->use_xchg && sum[1] > h->nranks - 0.5 && same_chunks && h->tpanels * h->tchunks + 1 <= h->sm_count + 2;
     return PRMF_OK;
 }
 
 int prmf_exchange_mode(const prmf_handle* h) {
     if (!h || !h->comm) return 0;
     if (!h->p2p_ready) return 1;
+    if (h->blk_xchg && h->use_block) return 4;
     return h->use_xchg ? 3 : 2;
 }
 
@@ -1847,6 +1998,14 @@ int prmf_kernel_times(prmf_handle* h, int reset, double* phase_ms, int64_t* phas
         if (phase_count) phase_count[i] = h->phase_n[i];
         if (reset) { h->phase_ms[i] = 0; h->phase_n[i] = 0; }
     }
+    return PRMF_OK;
+}
+
+int prmf_debug_inject_fault(prmf_handle* h, int kind) {
+    if (!h) return PRMF_ERR_ARG;
+    if (kind == 1) h->blk_n1 += 1;            // arrival targets of the next launch are one pass ahead of the counters
+    else if (kind == 2) h->blk_xseq += 1;     // this rank expects exchange flags one step ahead of what peers send
+    else return fail(h, PRMF_ERR_ARG, "unknown fault kind %d", kind);
     return PRMF_OK;
 }
 

@@ -207,8 +207,8 @@ class CudaEngine:
 
     @property
     def exchange_mode(self):
-        """"none" | "nccl" | "p2p-v-update" | "p2p-pass2": how the per-step sum over ranks is done."""
-        return ("none", "nccl", "p2p-v-update", "p2p-pass2")[int(self.lib.prmf_exchange_mode(self.h))]
+        """"none" | "nccl" | "p2p-v-update" | "p2p-pass2" | "p2p-push-block": how the per-step sum over ranks is done."""
+        return ("none", "nccl", "p2p-v-update", "p2p-pass2", "p2p-push-block")[int(self.lib.prmf_exchange_mode(self.h))]
 
     # -- introspection -------------------------------------------------------------------------------
     @property
@@ -224,6 +224,10 @@ class CudaEngine:
         n = (ctypes.c_int64 * _lib.N_PHASES)()
         self._ck(self.lib.prmf_kernel_times(self.h, 1 if reset else 0, ms, n))
         return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(_lib.PHASES)}
+
+    def inject_fault(self, kind):
+        """Testing aid (prmf_debug_inject_fault): make the next persistent step launch wait for something that never comes."""
+        self._ck(self.lib.prmf_debug_inject_fault(self.h, int(kind)))
 
     @property
     def stream(self):

@@ -266,11 +266,12 @@ def test_speculative_pass_is_bitwise_neutral(k):
 
 
 # ---- the launch-structure switches must not change results ----------------------------------------------
-@pytest.mark.parametrize("env", [{"PRMF_EPI": "0"}, {"PRMF_COOP": "0"}, {"PRMF_TMA": "0"}])
+@pytest.mark.parametrize("env", [{"PRMF_EPI": "0"}, {"PRMF_BLOCK": "0"}, {"PRMF_TMA": "0"}])
 @pytest.mark.parametrize("m,n,k,P", [(200, 517, 10, 12), (1000, 6750, 10, 20), (37, 131, 3, 5)])
 def test_launch_structure_switches(monkeypatch, env, m, n, k, P):
     """PRMF_EPI=0: separate U / V-update launches instead of the fused tails (the path of ranks without rows);
-    PRMF_COOP=0: plain launches of the fused-tail kernels; PRMF_TMA=0: the pre-TMA X-stream kernel."""
+    PRMF_BLOCK=0: two fused-tail launches per inner step instead of the persistent step kernel; PRMF_TMA=0: the
+    pre-TMA X-stream kernel."""
     from prmf_b200 import nmf_manifold_vec_update
     for key, val in env.items():
         monkeypatch.setenv(key, val)
@@ -351,6 +352,99 @@ def test_score_tables_large_and_small_pathways():
         for _ in range(size):
             a, b = rng.choice(genes, size=2, replace=False)
             G.add_edge(nodelist[a], nodelist[b], weight=float(rng.random() + 0.5))
+        Gs.append(G)
+    V = 3 * (1 - rng.random((n, k)))
+    mass, qn, qr = latent_pathway_tables(V, Gs, nodelist)
+    tables = O.PathwayTables(Gs, nodelist)
+    for c in range(k):
+        for p in range(len(Gs)):
+            np.testing.assert_allclose(np.sqrt(mass[c, p]) + 1 - qn[c, p], O.score_match(tables, V[:, c], p), rtol=1e-12)
+            np.testing.assert_allclose(qr[c, p], tables.Ls[p].dot(V[:, c]).dot(V[:, c]), rtol=1e-11)
+
+
+# ---- the persistent step kernel (block.cuh) -------------------------------------------------------------
+@pytest.mark.parametrize("m,n,k,P", [(300, 1200, 6, 9), (1500, 2100, 10, 12), (37, 131, 3, 5), (700, 523, 10, 9)])
+def test_persistent_step_kernel_matches_two_launch_path(monkeypatch, m, n, k, P):
+    """One cooperative launch per block of steps (default) against the two-launches-per-step path (PRMF_BLOCK=0) over
+    three blocks with the speculative pass on: same objective parts, score tables, U and V to rounding (the two
+    differ only in the order the U^T U partials of a share are added)."""
+    from prmf_b200 import CudaEngine, pack_pathways
+    X, nodelist, Gs, U, V, active = _instance(m, n, k, P, seed=3 * m + k, weighted=True)
+    packed = pack_pathways(Gs, nodelist)
+    results = []
+    for block in ("1", "0"):
+        monkeypatch.setenv("PRMF_BLOCK", block)
+        with CudaEngine(m, m, n, k) as eng:
+            eng.set_X(X); eng.set_pathways(packed); eng.set_UV(U, V)
+            log = []
+            for blk in range(3):
+                eng.set_active([(a + blk) % P for a in active])
+                eng.step_async(5, 2.0, 0.4)
+                parts, _, _, tables = eng.block_end(5, want_scores=True, prefetch=blk < 2)
+                log.append((parts.copy(), tables[0].copy(), tables[1].copy()) + eng.get_UV())
+            launches = eng.launch_count
+            results.append((log, launches))
+    (a, la), (b, lb) = results
+    assert la < lb, "the persistent path must launch fewer kernels (%d vs %d)" % (la, lb)
+    for x, y in zip(a, b):
+        for u, v in zip(x, y):
+            np.testing.assert_allclose(u, v, rtol=1e-11, atol=1e-13)
+
+
+def test_persistent_step_kernel_against_oracle_many_steps():
+    """Ten steps in one launch against the oracle (every step's objective parts)."""
+    from prmf_b200 import CudaEngine, pack_pathways
+    X, nodelist, Gs, U, V, active = _instance(900, 1300, 10, 14, seed=77, weighted=True)
+    Uo, Vo, parts_o, _, _, _ = oracle_block(X, U, V, Gs, nodelist, active, 10, 1.7, 0.6)
+    with CudaEngine(900, 900, 1300, 10) as eng:
+        eng.set_X(X); eng.set_pathways(pack_pathways(Gs, nodelist)); eng.set_UV(U, V); eng.set_active(active)
+        l0 = eng.launch_count
+        parts, _, _ = eng.step(10, 1.7, 0.6)
+        assert eng.launch_count - l0 <= 3, "10 steps = 1 persistent launch + the deferred objective (+ the active-set build)"
+        Ug, Vg = eng.get_UV()
+    np.testing.assert_allclose(parts[:, :5], parts_o, rtol=1e-9)
+    np.testing.assert_allclose(Ug, Uo, rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(Vg, Vo, rtol=1e-9, atol=1e-13)
+
+
+def test_bounded_wait_returns_timeout_instead_of_hanging(monkeypatch):
+    """A launch whose thread blocks wait for an arrival that never comes (injected) must end after the deadline with
+    PRMF_ERR_TIMEOUT, and the handle must refuse further steps."""
+    from prmf_b200 import CudaEngine, pack_pathways
+    from prmf_b200._lib import PrmfLibraryError
+    monkeypatch.setenv("PRMF_SPIN_TIMEOUT_MS", "200")
+    X, nodelist, Gs, U, V, active = _instance(300, 600, 6, 5, seed=4)
+    with CudaEngine(300, 300, 600, 6) as eng:
+        eng.set_X(X); eng.set_pathways(pack_pathways(Gs, nodelist)); eng.set_UV(U, V); eng.set_active(active)
+        eng.step(2, 1.0, 1.0)
+        eng.inject_fault(1)
+        import time
+        t0 = time.perf_counter()
+        with pytest.raises(PrmfLibraryError, match="wait expired"):
+            eng.step(2, 1.0, 1.0)
+        assert time.perf_counter() - t0 < 20
+        with pytest.raises(PrmfLibraryError, match="failed state"):
+            eng.step(1, 1.0, 1.0)
+
+
+def test_score_tables_pathway_larger_than_staging_buffer():
+    """A support too large for the shared-memory staging of scores_kernel takes the global-gather branch."""
+    import networkx as nx
+    from oracle import prmf_oracle as O
+    from prmf_b200 import latent_pathway_tables
+    rng = np.random.Generator(np.random.PCG64(13))
+    n, k = 4000, 10
+    nodelist = list(range(n))
+    Gs = []
+    for size in (2600, 30, 900):
+        genes = rng.choice(n, size=size, replace=False)
+        G = nx.Graph()
+        G.add_nodes_from(int(g) for g in genes)
+        for a, b in zip(genes[:-1], genes[1:]):
+            G.add_edge(int(a), int(b), weight=float(rng.random() + 0.5))
+        for _ in range(2 * size):
+            a, b = rng.choice(genes, size=2, replace=False)
+            G.add_edge(int(a), int(b), weight=float(rng.random() + 0.5))
         Gs.append(G)
     V = 3 * (1 - rng.random((n, k)))
     mass, qn, qr = latent_pathway_tables(V, Gs, nodelist)

@@ -266,7 +266,7 @@ class CpuReference:
     with the per-pathway n x n scipy matrices its `nmf_pathway` builds (:670-696) and its module-global table of
     normalised Laplacians.  kind "port": `oracle/prmf_oracle.py` when that install is absent."""
 
-    def __init__(self, Gs, nodelist, k):
+    def __init__(self, Gs, nodelist, k, force_port=False):
         from oracle import prmf_oracle as O
         self.O = O
         self.k = k
@@ -274,7 +274,7 @@ class CpuReference:
         self.tables = O.PathwayTables(Gs, nodelist)       # W, D, L, supports (as :678-690) + normalised Laplacians
         self.mod = None
         self.kind = "port"
-        if os.path.isfile(REF_SCRIPT):
+        if os.path.isfile(REF_SCRIPT) and not force_port:
             try:
                 self.mod = self._load_reference()
                 self.kind = "reference"
@@ -675,6 +675,8 @@ def parity_block(a, ctx, eng, Xh, lo, hi, Gs, nodelist, packed, U0, V0, gamma, d
            "gpu_survivors_sha256_16": hashlib.sha256(json.dumps(surv_ids, sort_keys=True).encode()).hexdigest()[:16],
            "gpu_survivors_per_factor": [len(surv_ids[kk]) for kk in sorted(surv_ids)]}
     cpu = None
+    if ctx.rank == 0 and not a.no_cpu_baseline and a.m * a.n > (1 << 29):
+        out["subsample"] = parity_subsample(a, eng, Gs, nodelist, packed, U0, V0)
     if ctx.rank == 0 and not a.no_cpu_baseline and a.m * a.n <= (1 << 29):
         use_all_cores()
         X = Xh.numpy() if (ctx.world == 1 and Xh is not None and Xh.dtype.is_floating_point and Xh.element_size() == 8) \
@@ -703,6 +705,44 @@ def parity_block(a, ctx, eng, Xh, lo, hi, Gs, nodelist, packed, U0, V0, gamma, d
                    "s_per_inner_step": r["s_per_inner_step"], "s_restrict": r["s_restrict"], "s_tables": ref.t_tables}
     ctx.barrier()
     return out, cpu
+
+
+def parity_subsample(a, eng_big, Gs, nodelist, packed, U0, V0, rows=2048):
+    """Instances too large for a CPU run at full shape (config 5): the first `rows` samples of the same matrix on a second,
+    single-GPU engine of the same mode against the CPU reference on those rows (a row subsample)."""
+    import torch
+    from prmf_b200 import CudaEngine
+    from prmf_b200.solver import init_latent_to_pathway_data, restrict_from_tables
+    rows = min(rows, a.m)
+    tf32 = a.x_dtype == "tf32"
+    Xs = (device_rows(0, rows, a.n, torch.float32 if tf32 else torch.float64) if a.x_gen == "device"
+          else torch.from_numpy(host_rows(0, rows, a.n, np.float32 if tf32 else np.float64)).cuda())
+    active = [kk % a.pathways for kk in range(a.k)]
+    with CudaEngine(rows, rows, a.n, a.k, device=torch.cuda.current_device(), x_dtype=a.x_dtype) as eng:
+        eng.set_X(Xs)
+        eng.set_pathways(packed)
+        normX = float(np.sqrt(eng.normX_sq))
+        gamma, delta = normX / a.k, 10 / normX
+        eng.set_UV(U0[:rows], V0)
+        eng.set_active(active)
+        parts, _, _ = eng.step(a.cpu_inner_steps, gamma, delta)
+        Ug, Vg = eng.get_UV()
+        mass, qn, _ = eng.scores()
+    surv = restrict_from_tables(mass, qn, init_latent_to_pathway_data(a.k, packed.P))
+    surv_ids = {kk: [int(p) for p, _ in v] for kk, v in surv.items()}
+    X = Xs.cpu().numpy().astype(np.float64)
+    if tf32:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from helpers import tf32_round
+        X = tf32_round(X.astype(np.float32))
+    use_all_cores()
+    ref = CpuReference(Gs, nodelist, a.k, force_port=True)       # the port: 2 000 n x n DOK matrices take minutes to build
+    r = cpu_sample(ref, X, U0[:rows], V0, active, a.cpu_inner_steps, gamma, delta, normX)
+    same = all(surv_ids[kk] == r["survivors"][kk] for kk in surv_ids)
+    return {"rows": rows, "vs": "oracle port (oracle/prmf_oracle.py) on the first %d samples" % rows,
+            "U_max_rel_err": rel_err(Ug, r["U"]), "V_max_rel_err": rel_err(Vg, r["V"]),
+            "obj_parts_max_rel_err": rel_err(parts[:, :5], r["parts"]), "restrict_survivors_identical": bool(same),
+            "tolerance": "tf32 mode: obj parts 1e-4, U/V 1e-3 (not the parity mode)" if tf32 else "fp64: 1e-9 / 1e-8"}
 
 
 def time_to_converge(a, ctx, X_local, lo, Gs, nodelist, packed, steady_value):

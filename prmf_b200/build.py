@@ -15,7 +15,8 @@ LIB = os.path.join(HERE, "libprmf_b200.so")
 HEADER = os.path.join(HERE, "..", "include", "prmf_b200.h")
 # translation unit -> headers it depends on
 SOURCES = {
-    "prmf_b200.cu": ["kernels.cuh", "fused.cuh", "tf32.cuh", "nccl_dyn.h"],
+    "prmf_b200.cu": ["kernels.cuh", "block_params.h", "fused.cuh", "tf32.cuh", "nccl_dyn.h"],
+    "block.cu": ["kernels.cuh", "block_params.h", "block.cuh"],
     "preprocess.cu": [],
     "cv.cu": [],
     "host_logic.cpp": [],
@@ -118,5 +119,28 @@ def _build_locked(force, verbose):
     return LIB
 
 
+def build_debug_library(defines, out_path, sources=("block.cu",)):
+    """Developer builds with instrumentation macros (tools/*.py): a second library next to the product one, e.g.
+    python -m prmf_b200.build --debug PRMF_BLOCK_TIMING  ->  tools/libprmf_dbg.so  (recompiles `sources` with -D...)"""
+    build_library()
+    nvcc = nvcc_path()
+    objs = []
+    for src in SOURCES:
+        if src not in sources:
+            objs.append(_obj(src))
+            continue
+        obj = os.path.join(OBJDIR, os.path.splitext(src)[0] + "_dbg.o")
+        cmd = [nvcc, "-O3", "-std=c++17"] + ARCH + ["-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off"] + \
+              ["-D" + d for d in defines] + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        subprocess.run(cmd, check=True)
+        objs.append(obj)
+    subprocess.run([nvcc, "-shared"] + ARCH + ["-o", out_path] + objs + ["-ldl"], check=True)
+    return out_path
+
+
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--debug" in sys.argv:
+        defs = sys.argv[sys.argv.index("--debug") + 1:]
+        print(build_debug_library(defs, os.path.join(HERE, "..", "tools", "libprmf_dbg.so")))
+    else:
+        print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -10,77 +10,20 @@
 //     the small W operand (rows of V / U_new) waits for the data dependency, a monotone counter in L2;
 //   * kernel boundaries are replaced by those counters: `udone` (all sample panels updated and folded) gates the
 //     W rows of pass 2 and the V update; `vdone` gates the W rows of the next pass 1 and the next U update;
-//   * on several GPUs the sum over ranks of [X^T U | U^T U] is part of the pass-2 tail: every CTA pushes the sums of
-//     its share of genes straight into every peer's receive buffer (NVLink stores), raises a flag there, waits for
-//     the same share from every peer and adds the ranks' contributions in rank order from LOCAL memory -- one
-//     one-way hop, bitwise identical on all ranks, no collective launch.  U^T U is pushed at the START of pass 2
-//     (it is complete after pass 1), so it has the whole pass to arrive.
+//   * on several GPUs the sum over ranks of [X^T U | U^T U] is part of the pass-2 tail: every thread pushes the sums it
+//     owns straight into every peer's receive buffer as 16-byte {value, sequence number} entries (one NVLink store
+//     each, no fence, no flag) and polls the same entries of all ranks in its OWN memory until their sequence number is
+//     this step's, adding them in rank order -- one one-way hop, bitwise identical on all ranks, no collective launch.
+//     U^T U is pushed at the START of pass 2 (it is complete after pass 1), so it has the whole pass to arrive.
 // Every spin wait has a %globaltimer deadline: on expiry the kernel sets an error word, stops waiting and drains;
 // the host reports PRMF_ERR_TIMEOUT instead of hanging (dead peer, lost launch).
 // The objective is deferred exactly as on the two-launch path: every step leaves its Gram partials, U^T U and the
 // active-set values of V_new in per-step slots; objective_deferred_kernel evaluates the block afterwards.
 #pragma once
 
-#include "kernels.cuh"
+#include "block_params.h"
 
 namespace prmf {
-
-constexpr int kBlkRS = 8;            // rows of M per ring stage (as skinny_tma_kernel<.,8,.>)
-constexpr int kBlkTile = 64;         // rows of a share updated per sub-tile of the tail (bounds the scratch)
-
-constexpr unsigned int kErrTimeoutLocal = 1u;   // a wait on another CTA of this GPU expired
-constexpr unsigned int kErrTimeoutPeer = 2u;    // a wait on a peer GPU's flag expired
-
-struct BlockParams {
-    // X (m x n, leading dimension ldx) and its transposed copy (n x m, ldxt)
-    const double* X;
-    const double* Xt;
-    int64_t ldx, ldxt, m, n;
-    // pass 1: column panels over samples, row chunks over genes; pass 2: panels over genes, chunks over samples
-    int panels1, panel_w1, chunks1;
-    int panels2, panel_w2, chunks2;
-    int64_t rpc1, rpc2;
-    int stages;
-    uint32_t ring_stage_bytes;       // max over the two passes of (RS * panel_w * 8 + W rows, 128-byte padded)
-    // state: U[0] / V[0] are current at launch; every pass 1 flips U, every pass 2 flips V
-    double* U[2];
-    double* V[2];
-    double* Apart;                   // [chunks1][m][K]
-    double* Bpart;                   // [chunks2][n][K]
-    double* Gu_part;                 // [panels1][K*K]   U_new^T U_new per sample panel (this rank's rows)
-    double* part2;                   // scratch [tiles][K*K] per-CTA Gram partials
-    double* vb2;                     // scratch [tiles]
-    const double* Gv0;               // V^T V of the V at block start (for the U update of half 0)
-    // monotone counters (never reset): arrive / done per panel, and the two grid-wide ones
-    unsigned long long* arrive1;
-    unsigned long long* done1;
-    unsigned long long* arrive2;
-    unsigned long long* done2;
-    unsigned long long* udone;       // += 1 per folded sample panel
-    unsigned long long* vdone;       // += 1 per folded gene panel
-    unsigned long long base1, base2; // pass-1 / pass-2 executions of this kernel on this handle before this launch
-    int h0, nh;                      // halves [h0, h0 + nh) of the block: even = pass 1, odd = pass 2; step = half / 2
-    // V update
-    Pathways pw;
-    const int32_t* active;
-    const int32_t* pos;
-    const double* gd;
-    // deferred objective: per-step slots
-    double* hist_Gu;                 // [steps][K*K]
-    double* hist_Gvp;                // [steps][panels2][K*K]
-    double* hist_VBp;                // [steps][panels2]
-    double* hist_vh;                 // [steps][kVhCap]
-    const int64_t* doff;
-    // bounded waits
-    unsigned int* err;
-    unsigned long long timeout_ns;
-    // exchange over ranks (nranks <= 1: none)
-    int nranks, rank;
-    double* xbuf[kMaxPeers];         // rank r's receive buffer: [parity 2][src rank kMaxPeers][xcount]
-    unsigned long long* xflag[kMaxPeers];   // rank r's flags: [src rank kMaxPeers][tiles2 + 1]
-    size_t xcount;                   // doubles per (parity, src) slot: n*K + K*K, padded
-    unsigned long long xbase;        // exchanges (= pass-2 executions of this kernel) before this launch
-};
 
 __device__ __forceinline__ unsigned long long blk_gtime() {
     unsigned long long t;
@@ -104,6 +47,7 @@ __device__ __forceinline__ bool blk_wait_ge(const unsigned long long* p, unsigne
     for (;;) {
         const unsigned long long v = SYS ? ld_acquire_sys_u64(p) : ld_acquire_gpu_u64(p);
         if (v >= target) return true;
+        __nanosleep(40);                          // a spinning warp costs issue slots and power on its SM
         if ((++polls & 255u) == 0u) {
             const unsigned long long now = blk_gtime();
             if (t0 == 0) t0 = now;
@@ -113,6 +57,33 @@ __device__ __forceinline__ bool blk_wait_ge(const unsigned long long* p, unsigne
             }
         }
     }
+}
+
+// Low-latency exchange entries: a value travels with its sequence number in ONE 16-byte store, so the receiver needs
+// neither a fence nor a separate flag -- it polls the entry itself until the sequence number is the expected one
+// (one one-way NVLink hop; the pattern of NCCL's LL protocol, here with 8-byte payloads).
+__device__ __forceinline__ void ll_store(ulonglong2* dst, double v, unsigned long long seq) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(__double_as_longlong(v)), "l"(seq) : "memory");
+}
+
+__device__ __forceinline__ double ll_wait(const ulonglong2* src, unsigned long long seq, unsigned int* err,
+                                          unsigned long long timeout_ns) {
+    unsigned long long t0 = 0, lo, hi;
+    unsigned int polls = 0;
+    for (;;) {
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(src) : "memory");
+        if (hi == seq) break;
+        __nanosleep(20);
+        if ((++polls & 255u) == 0u) {
+            const unsigned long long now = blk_gtime();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > timeout_ns || ld_volatile_u32(err) != 0u) {
+                atomicOr(err, kErrTimeoutPeer);
+                break;
+            }
+        }
+    }
+    return __longlong_as_double((long long)lo);
 }
 
 // per-thread running Gram accumulation over the sub-tiles of a share (thread = (pair a,b ; row slice))
@@ -176,8 +147,35 @@ __device__ __forceinline__ void blk_share(const BlkTile& tl, int chunks, int64_t
     rows = max(0, min(all, rb + per) - rb);
 }
 
+#ifdef PRMF_BLOCK_TIMING
+// Developer instrumentation (not in the product build): %globaltimer stamps per CTA and half:
+// [0] half entered  [1] first ring stage landed  [2] main loop done  [3] panel complete (arrive barrier passed)
+// [4] sums over ranks done (pass 2, sharded)  [5] share updated  [6] tail done  [7] producer: W dependency satisfied
+constexpr int kBlkDbgHalves = 24;
+__device__ unsigned long long g_blk_dbg[160 * kBlkDbgHalves * 8];
+#define BLK_STAMP(i_half, slot) do { if ((threadIdx.x & 255) == 0 && (i_half) < kBlkDbgHalves) \
+        g_blk_dbg[((size_t)blockIdx.x * kBlkDbgHalves + (i_half)) * 8 + (slot)] = blk_gtime(); } while (0)
+#define BLK_STAMP_P(i_half, slot) do { if (lane == 0 && (i_half) < kBlkDbgHalves) \
+        g_blk_dbg[((size_t)blockIdx.x * kBlkDbgHalves + (i_half)) * 8 + (slot)] = blk_gtime(); } while (0)
+#else
+#define BLK_STAMP(i_half, slot) do { } while (0)
+#define BLK_STAMP_P(i_half, slot) do { } while (0)
+#endif
+
+__device__ __forceinline__ void red_release_add(unsigned long long* p, unsigned long long v) {
+    // release-add: the writes this CTA made before the preceding barrier are visible to whoever acquires the counter
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long atom_acq_rel_add(unsigned long long* p, unsigned long long v) {
+    unsigned long long old;
+    asm volatile("atom.acq_rel.gpu.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
+    return old;
+}
+// consumers (256) + helper warp (32): the helper's prefetched operands are in shared memory
+__device__ __forceinline__ void tail_bar() { asm volatile("bar.sync 2, 288;" ::: "memory"); }
+
 template <int K>
-__global__ void __launch_bounds__(kTmaThreads, 1)
+__global__ void __launch_bounds__(kBlkThreads, 1)
 block_kernel(const BlockParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int stages = p.stages;
@@ -187,7 +185,23 @@ block_kernel(const BlockParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x;
     constexpr uint32_t w_bytes = (uint32_t)kBlkRS * K * 8u;
+    constexpr int KK = K * K;
     __shared__ int s_last;
+    // scratch: Gv | Gu (128 each) | 8 slice sums of a Gram | tail arrays
+    double* sGv = scratch;                                 // V^T V of the current V (U update)
+    double* sGu = scratch + 128;                           // U_new^T U_new, summed over ranks (V update)
+    double* sW8 = sGu + 112;                               // 8 warp sums (K*K <= 100 < 112)
+    double* sBuf = scratch + 256;                          // 8 * K*K slice sums
+    // tail arrays, all views of the same kBlkRowsCap x K doubles:
+    double* sR = sBuf + 8 * KK;                            // large shares: old rows, then the new ones (kBlkRowsCap x K)
+    double* sT = sR;                                       // small shares: new rows | sums of the pass partials | old rows
+    double* sS = sT + kBlkTile * K;                        //   (three arrays of kBlkTile x K)
+    double* sO = sS + kBlkTile * K;
+    double* pT = sR;                                       // pass 2 with the helper warp's prefetch (five arrays of kBlkPre x K):
+    double* pS = pT + kBlkPre * K;                         //   new rows | sums | old rows | W.v of the active pathway | degree
+    double* pO = pS + kBlkPre * K;
+    double* pWv = pO + kBlkPre * K;
+    double* pDg = pWv + kBlkPre * K;
 
     if (threadIdx.x == 0) {
         for (int s2 = 0; s2 < stages; ++s2) {
@@ -200,6 +214,13 @@ block_kernel(const BlockParams p) {
 
     const BlkTile t1 = blk_tile(b, p.panels1, p.panel_w1, p.chunks1, p.rpc1, p.n, p.ldxt);   // M = Xt: n rows, m columns
     const BlkTile t2 = blk_tile(b, p.panels2, p.panel_w2, p.chunks2, p.rpc2, p.m, p.ldx);    // M = X:  m rows, n columns
+    const unsigned long long tiles1 = (unsigned long long)p.panels1 * p.chunks1;
+    const unsigned long long tiles2 = (unsigned long long)p.panels2 * p.chunks2;
+    int rb1, rows1, rb2, rows2;
+    blk_share(t1, p.chunks1, p.m, rb1, rows1);
+    blk_share(t2, p.chunks2, p.n, rb2, rows2);
+    const bool helper_on = (p.flags & 1u) == 0u;
+    const bool pre2 = helper_on && t2.in && rows2 <= kBlkPre;   // the helper warp prefetches the V update's operands
 
     if (warp == kTmaConsumerWarps) {
         // ================================= producer warp =================================
@@ -223,9 +244,9 @@ block_kernel(const BlockParams p) {
             if (tl.iters > 0) {
                 const uint32_t row_bytes = (uint32_t)tl.width * 8u;
                 const uint32_t x_stage_bytes = (uint32_t)kBlkRS * (uint32_t)panel_w * 8u;
-                // the data dependency of the W rows: every panel of the previous half folded
+                // the data dependency of the W rows: every CTA of the previous half has stored its share
                 const unsigned long long* dep = pass1 ? p.vdone : p.udone;
-                const unsigned long long dep_target = pass1 ? (n2 * (unsigned long long)p.panels2) : (n1 * (unsigned long long)p.panels1);
+                const unsigned long long dep_target = pass1 ? n2 * tiles2 : n1 * tiles1;
                 const int pre = min(stages, tl.iters);
                 // X tiles of the first `pre` stages: no dependency, they go out as soon as the ring slots are free
                 {
@@ -246,6 +267,7 @@ block_kernel(const BlockParams p) {
                     }
                 }
                 if (lane == 0) blk_wait_ge<false>(dep, dep_target, p.err, p.timeout_ns);
+                BLK_STAMP_P(i, 7);
                 __syncwarp();
                 for (int it = 0; it < pre; ++it) {
                     const int64_t r0 = tl.rbeg + (int64_t)it * kBlkRS;
@@ -273,14 +295,104 @@ block_kernel(const BlockParams p) {
         return;
     }
 
+    if (warp == kTmaConsumerWarps + 1) {
+        // ================================= helper warp =================================
+        // While the consumer warps stream the pass, this warp fetches what their tail will need, so that the tail
+        // itself is left with one round of loads (the pass partials): the Gram of the other factor matrix, and for
+        // the V update the old rows of the share and the sparse terms of the active pathways (a chain of five
+        // dependent gathers per entry: pos -> row_ptr -> col_local -> support_idx -> V).
+        unsigned long long n1 = p.base1, n2 = p.base2;
+        int vi = 0;
+        for (int i = 0; i < p.nh; ++i) {
+            const int half = p.h0 + i;
+            const bool pass1 = (half & 1) == 0;
+            const int step = half >> 1;
+            if (pass1) {
+                ++n1;
+                if (!t1.in) continue;
+                if (half == 0) {
+                    for (int e = lane; e < KK; e += 32) sGv[e] = p.Gv0[e];
+                } else {
+                    if (lane == 0) blk_wait_ge<false>(p.vfold, n2 * (unsigned long long)p.panels2, p.err, p.timeout_ns);
+                    __syncwarp();
+                    for (int e = lane; e < KK; e += 32)
+                        sGv[e] = sum_strided_cg(p.hist_Gvp + (size_t)(step - 1) * p.panels2 * KK + e, p.panels2, KK);
+                }
+                tail_bar();
+                continue;
+            }
+            ++n2;
+            const double* Vold = p.V[vi];
+            vi ^= 1;
+            if (!t2.in) continue;
+            // U^T U: this rank's folded panel partials (complete once ufold reached this step's pass 1), then over ranks
+            if (lane == 0) blk_wait_ge<false>(p.ufold, n1 * (unsigned long long)p.panels1, p.err, p.timeout_ns);
+            __syncwarp();
+            const unsigned long long xs = p.xbase + (n2 - p.base2);                 // this exchange's sequence number
+            const size_t xpar = (size_t)(xs & 1ull) * kMaxPeers;
+            if (p.nranks <= 1) {
+                for (int e = lane; e < KK; e += 32) {
+                    const double g = sum_strided_cg(p.Gu_part + e, p.panels1, KK);
+                    sGu[e] = g;
+                    if (b == 0) p.hist_Gu[(size_t)step * KK + e] = g;
+                }
+            } else {
+                if (b == 0) {                      // CTA 0 pushes this rank's U^T U to every peer: it has the whole pass to arrive
+                    const size_t slot = (xpar + p.rank) * p.xcount + (size_t)p.n * K;
+                    for (int e = lane; e < KK; e += 32) {
+                        const double g = sum_strided_cg(p.Gu_part + e, p.panels1, KK);
+                        for (int r = 0; r < p.nranks; ++r) ll_store(p.xbuf[r] + slot + e, g, xs);
+                    }
+                }
+                for (int e = lane; e < KK; e += 32) {
+                    double g = 0.0;
+                    for (int r = 0; r < p.nranks; ++r)
+                        g += ll_wait(p.xbuf[p.rank] + (xpar + r) * p.xcount + (size_t)p.n * K + e, xs, p.err, p.timeout_ns);
+                    sGu[e] = g;
+                    if (b == 0) p.hist_Gu[(size_t)step * KK + e] = g;
+                }
+            }
+            if (pre2) {
+                // round 1: the old rows and the row map of every entry this lane owns, all loads in flight at once;
+                // round 2: the few entries inside an active pathway (about 1 % of them) walk their packed CSR row
+                constexpr int PER = (kBlkPre * K + 31) / 32;
+                const int n_el = rows2 * K;
+                const int64_t base = (t2.c0 + rb2) * K;
+                double vo[PER];
+                int32_t prs[PER];
+#pragma unroll
+                for (int q = 0; q < PER; ++q) {
+                    const int e = lane + 32 * q;
+                    const bool ok = e < n_el;
+                    vo[q] = ok ? __ldcg(Vold + base + e) : 0.0;
+                    prs[q] = ok ? __ldg(p.pos + base + e) : -1;
+                }
+#pragma unroll
+                for (int q = 0; q < PER; ++q) {
+                    const int e = lane + 32 * q;
+                    if (e >= n_el) continue;
+                    const int c = e % K;
+                    double wv = 0.0, dg = -1.0;                                                  // dg < 0: not in the support
+                    const int32_t pr = prs[q];
+                    if (pr >= 0) {
+                        const Pathways& pw = p.pw;
+                        const int64_t pbase = pw.path_ptr[p.active[c]];
+                        for (int64_t e2 = pw.row_ptr[pr]; e2 < pw.row_ptr[pr + 1]; ++e2)
+                            wv = fma(pw.w[e2], __ldcg(Vold + (int64_t)pw.support_idx[pbase + pw.col_local[e2]] * K + c), wv);
+                        dg = pw.deg[pr];
+                    }
+                    pO[e] = vo[q];
+                    pWv[e] = wv;
+                    pDg[e] = dg;
+                }
+            }
+            tail_bar();
+        }
+        return;
+    }
+
     // ================================= consumer warps =================================
     const int t = threadIdx.x;                             // 0..255
-    double* sG = scratch;                                  // K*K Gram of the other factor matrix (padded to 128)
-    double* sW8 = sG + 112;                                // 8 warp sums
-    double* sBuf = sG + 128;                               // 8 * K*K slice sums
-    double* sT = sBuf + 8 * K * K;                         // kBlkTile x K new rows
-    double* sS = sT + kBlkTile * K;                        // kBlkTile x K sums of the pass partials
-    double* sO = sS + kBlkTile * K;                        // kBlkTile x K old rows
     int s2 = 0;
     uint32_t phase = 0;
     unsigned long long n1 = p.base1, n2 = p.base2;
@@ -295,22 +407,7 @@ block_kernel(const BlockParams p) {
         const int64_t cols = pass1 ? p.m : p.n;            // columns of M = rows of the matrix being updated
         double* OutPart = pass1 ? p.Apart : p.Bpart;
         if (pass1) ++n1; else ++n2;
-
-        // on several GPUs CTA 0 pushes this rank's U^T U to every peer at the start of pass 2 (complete since pass 1)
-        if (!pass1 && p.nranks > 1 && b == 0) {
-            if (t == 0) blk_wait_ge<false>(p.udone, n1 * (unsigned long long)p.panels1, p.err, p.timeout_ns);
-            cons_bar();
-            const unsigned long long xs = p.xbase + (n2 - p.base2);
-            const size_t slot = ((size_t)(xs & 1ull) * kMaxPeers + p.rank) * p.xcount + (size_t)p.n * K;
-            if (t < K * K) {
-                const double g = sum_strided_cg(p.Gu_part + t, p.panels1, K * K);
-                for (int r = 0; r < p.nranks; ++r) p.xbuf[r][slot + t] = g;
-            }
-            __threadfence_system();
-            cons_bar();
-            if (t < p.nranks)
-                st_release_sys_u64(p.xflag[t] + (size_t)p.rank * (p.panels2 * p.chunks2 + 1) + p.panels2 * p.chunks2, xs);
-        }
+        BLK_STAMP(i, 0);
 
         // ---- main loop: acc[g][c] += M[row][col g] * W[row][c] over the chunk's rows ----
         if (tl.in) {
@@ -326,6 +423,7 @@ block_kernel(const BlockParams p) {
             for (int it = 0; it < tl.iters; ++it) {
                 const int rows = (int)min((int64_t)kBlkRS, tl.rend - (tl.rbeg + (int64_t)it * kBlkRS));
                 mbar_wait(&full_bar[s2], phase);
+                if (it == 0) BLK_STAMP(i, 1);
                 const unsigned char* sx = smem_raw + (size_t)s2 * p.ring_stage_bytes;
                 const double* sw = reinterpret_cast<const double*>(sx + x_stage_bytes);
                 if (rows == kBlkRS) {
@@ -334,9 +432,20 @@ block_kernel(const BlockParams p) {
                         const double2* xrow = reinterpret_cast<const double2*>(sx + (size_t)r * panel_w * 8);
                         const double2 xa = act ? xrow[t] : make_double2(0.0, 0.0);
                         const double2 xb = act2 ? xrow[t + H] : make_double2(0.0, 0.0);
+                        // the W row as 128-bit broadcast reads (the ring stage stride is a run-time value, so the
+                        // compiler cannot prove the 16-byte alignment of sw itself; K even => every row is aligned)
+                        double wr[K];
+                        if constexpr (K % 2 == 0) {
+                            const double2* sw2 = reinterpret_cast<const double2*>(sw + r * K);
+#pragma unroll
+                            for (int c = 0; c < K / 2; ++c) { const double2 w2 = sw2[c]; wr[2 * c] = w2.x; wr[2 * c + 1] = w2.y; }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < K; ++c) wr[c] = sw[r * K + c];
+                        }
 #pragma unroll
                         for (int c = 0; c < K; ++c) {
-                            const double u = sw[r * K + c];
+                            const double u = wr[c];
                             acc[0][c] = fma(xa.x, u, acc[0][c]);
                             acc[1][c] = fma(xa.y, u, acc[1][c]);
                             acc[2][c] = fma(xb.x, u, acc[2][c]);
@@ -373,184 +482,220 @@ block_kernel(const BlockParams p) {
                 }
             }
         }
+        BLK_STAMP(i, 2);
 
         // ---- tail: this CTA's share of the panel's rows ----
+        // Element e = t + 256 q of a tile of <= kBlkRowsCap rows belongs to thread t (q < K): the pass partials and the old
+        // rows are read as contiguous runs (fully used sectors), the sums stay in registers, the old rows go through shared
+        // memory because an entry needs its whole row for the k x k contraction; the new rows replace them there for the Gram.
         if (pass1) {
             const double* Uold = p.U[ui];
             double* Unew = p.U[ui ^ 1];
             ui ^= 1;
             if (!tl.in) continue;
-            int rb, rows;
-            blk_share(tl, chunks, cols, rb, rows);
-            // Gv of the current V: the published one for the first half of a block, else the per-panel partials the
-            // previous step's V update left (complete once vdone reached the previous pass 2)
-            if (half == 0) {
-                if (t < K * K) sG[t] = p.Gv0[t];
-            } else {
-                if (t == 0) blk_wait_ge<false>(p.vdone, n2 * (unsigned long long)p.panels2, p.err, p.timeout_ns);
-                cons_bar();
-                if (t < K * K)
-                    sG[t] = sum_strided_cg(p.hist_Gvp + (size_t)(step - 1) * p.panels2 * K * K + t, p.panels2, K * K);
-            }
-            // every CTA of the panel has stored its partials
-            __threadfence();
+            const int rb = rb1, rows = rows1;
+            // every CTA of the panel has stored its partials (release-add after the barrier: cumulative over the CTA's stores)
             cons_bar();
             if (t == 0) {
-                atomicAdd(p.arrive1 + tl.panel, 1ull);
+                red_release_add(p.arrive1 + tl.panel, 1ull);
                 blk_wait_ge<false>(p.arrive1 + tl.panel, n1 * (unsigned long long)chunks, p.err, p.timeout_ns);
             }
-            cons_bar();
+            tail_bar();                                     // + the helper warp: sGv is ready
+            BLK_STAMP(i, 3);
             BlkGram<K> gram;
-            for (int r0 = 0; r0 < rows; r0 += kBlkTile) {
-                const int nr = min(kBlkTile, rows - r0);
-                const int n_el = nr * K;
-                const int64_t base = (tl.c0 + rb + r0) * K;
-                for (int e = t; e < n_el; e += 256) sO[e] = __ldcg(Uold + base + e);
-                epi_stage_sums(sS, p.Apart + base, n_el, chunks, cols * K);                      // X.V   (:420)
-                cons_bar();
-                for (int e = t; e < n_el; e += 256) {
-                    const int r = e / K, c = e - r * K;
-                    const double* urow = sO + r * K;
-                    double den = 0.0;
-#pragma unroll
-                    for (int l = 0; l < K; ++l) den = fma(urow[l], sG[l * K + c], den);
-                    const double u = urow[c];
-                    den += u;
-                    const double f = (den != 0.0) ? sS[e] / den : 1.0;                           // 0/0 := 1 (:422)
-                    const double un = u * f;
-                    sT[e] = un;
-                    Unew[base + e] = un;
+            if (chunks <= 8) {
+                // few chunks, large shares (1-2 GPUs): entry e = t + 256 q of a tile belongs to thread t (q < K); partials and old
+                // rows are read as contiguous runs with every load of the thread in flight at once, the sums stay in registers
+                for (int r0 = 0; r0 < rows; r0 += kBlkRowsCap) {
+                    const int nr = min(kBlkRowsCap, rows - r0);
+                    const int n_el = nr * K;
+                    const int64_t base = (tl.c0 + rb + r0) * K;
+                    double a[K];
+    #pragma unroll
+                    for (int q = 0; q < K; ++q) {
+                        const int e = t + 256 * q;
+                        a[q] = 0.0;
+                        if (e < n_el) sR[e] = __ldcg(Uold + base + e);
+                    }
+    #pragma unroll 4
+                    for (int ch = 0; ch < chunks; ++ch) {                                            // X.V (:420), chunk order
+                        const double* src = p.Apart + (int64_t)ch * cols * K + base;
+    #pragma unroll
+                        for (int q = 0; q < K; ++q) {
+                            const int e = t + 256 * q;
+                            if (e < n_el) a[q] += __ldcg(src + e);
+                        }
+                    }
+                    cons_bar();
+                    double un[K];
+    #pragma unroll
+                    for (int q = 0; q < K; ++q) {
+                        const int e = t + 256 * q;
+                        un[q] = 0.0;
+                        if (e < n_el) {
+                            const int r = e / K, c = e - r * K;
+                            const double* urow = sR + r * K;
+                            double den = 0.0;
+    #pragma unroll
+                            for (int l = 0; l < K; ++l) den = fma(urow[l], sGv[l * K + c], den);
+                            const double u = urow[c];
+                            den += u;
+                            const double f = (den != 0.0) ? a[q] / den : 1.0;                        // 0/0 := 1 (:422)
+                            un[q] = u * f;
+                            Unew[base + e] = un[q];
+                        }
+                    }
+                    cons_bar();
+                    // the share of U_new is stored: release the W rows of pass 2 (the Gram partial below is off that path)
+                    if (r0 + kBlkRowsCap >= rows && t == 0) red_release_add(p.udone, 1ull);
+    #pragma unroll
+                    for (int q = 0; q < K; ++q) {
+                        const int e = t + 256 * q;
+                        if (e < n_el) sR[e] = un[q];
+                    }
+                    cons_bar();
+                    gram.add(sR, nr);
+                    cons_bar();
                 }
-                cons_bar();
-                gram.add(sT, nr);
-                cons_bar();
+            } else {
+                // many chunks, small shares: sums staged 16 partials at a time (epi_stage_sums)
+                for (int r0 = 0; r0 < rows; r0 += kBlkTile) {
+                    const int nr = min(kBlkTile, rows - r0);
+                    const int n_el = nr * K;
+                    const int64_t base = (tl.c0 + rb + r0) * K;
+                    for (int e = t; e < n_el; e += 256) sO[e] = __ldcg(Uold + base + e);
+                    epi_stage_sums(sS, p.Apart + base, n_el, chunks, cols * K);                  // X.V   (:420)
+                    cons_bar();
+                    for (int e = t; e < n_el; e += 256) {
+                        const int r = e / K, c = e - r * K;
+                        const double* urow = sO + r * K;
+                        double den = 0.0;
+#pragma unroll
+                        for (int l = 0; l < K; ++l) den = fma(urow[l], sGv[l * K + c], den);
+                        const double u = urow[c];
+                        den += u;
+                        const double f = (den != 0.0) ? sS[e] / den : 1.0;                       // 0/0 := 1 (:422)
+                        const double un = u * f;
+                        sT[e] = un;
+                        Unew[base + e] = un;
+                    }
+                    cons_bar();
+                    if (r0 + kBlkTile >= rows && t == 0) red_release_add(p.udone, 1ull);
+                    gram.add(sT, nr);
+                    cons_bar();
+                }
             }
+            if (rows == 0 && t == 0) red_release_add(p.udone, 1ull);
+            BLK_STAMP(i, 5);
             const int64_t me = (int64_t)tl.panel * chunks + tl.chunk;
-            gram.finish(sBuf, p.part2 + me * K * K);
-            __threadfence();
+            gram.finish(sBuf, p.part2 + me * KK);
             cons_bar();
             if (t == 0) {
-                const unsigned long long prev = atomicAdd(p.done1 + tl.panel, 1ull);
+                const unsigned long long prev = atom_acq_rel_add(p.done1 + tl.panel, 1ull);
                 s_last = prev + 1ull == n1 * (unsigned long long)chunks;
             }
             cons_bar();
             if (s_last) {                                   // last CTA of the panel: fold the panel's Gram partials
-                __threadfence();
-                if (t < K * K)
-                    p.Gu_part[(int64_t)tl.panel * K * K + t] =
-                        sum_strided_cg(p.part2 + (int64_t)tl.panel * chunks * K * K + t, chunks, K * K);
-                __threadfence();
+                if (t < KK)
+                    p.Gu_part[(int64_t)tl.panel * KK + t] = sum_strided_cg(p.part2 + (int64_t)tl.panel * chunks * KK + t, chunks, KK);
                 cons_bar();
-                if (t == 0) atomicAdd(p.udone, 1ull);
+                if (t == 0) red_release_add(p.ufold, 1ull);
             }
-            cons_bar();                                     // s_last is rewritten by the next tail
+            cons_bar();                                     // s_last / sR are rewritten by the next tail
+            BLK_STAMP(i, 6);
         } else {
             const double* Vold = p.V[vi];
             double* Vnew = p.V[vi ^ 1];
             vi ^= 1;
             if (!tl.in) continue;
-            int rb, rows;
-            blk_share(tl, chunks, cols, rb, rows);
-            const int tiles2 = p.panels2 * p.chunks2;
+            const int rb = rb2, rows = rows2;
             const unsigned long long xs = p.xbase + (n2 - p.base2);                 // this exchange's sequence number
             const size_t xpar = (size_t)(xs & 1ull) * kMaxPeers;
-            // Gu = U_new^T U_new: sum over this rank's sample panels (complete once udone reached this step's pass 1),
-            // then over ranks
-            if (t == 0) blk_wait_ge<false>(p.udone, n1 * (unsigned long long)p.panels1, p.err, p.timeout_ns);
-            cons_bar();
-            if (p.nranks <= 1) {
-                if (t < K * K) {
-                    const double g = sum_strided_cg(p.Gu_part + t, p.panels1, K * K);
-                    sG[t] = g;
-                    if (b == 0) p.hist_Gu[(size_t)step * K * K + t] = g;
-                }
-            } else {
-                if (t < p.nranks)
-                    blk_wait_ge<true>(p.xflag[p.rank] + (size_t)t * (tiles2 + 1) + tiles2, xs, p.err, p.timeout_ns);
-                cons_bar();
-                if (t < K * K) {
-                    double g = 0.0;
-                    for (int r = 0; r < p.nranks; ++r) g += __ldcg(p.xbuf[p.rank] + (xpar + r) * p.xcount + (size_t)p.n * K + t);
-                    sG[t] = g;
-                    if (b == 0) p.hist_Gu[(size_t)step * K * K + t] = g;
-                }
-            }
             const double gamma = p.gd[0], delta = p.gd[1];
-            __threadfence();
             cons_bar();
             if (t == 0) {
-                atomicAdd(p.arrive2 + tl.panel, 1ull);
+                red_release_add(p.arrive2 + tl.panel, 1ull);
                 blk_wait_ge<false>(p.arrive2 + tl.panel, n2 * (unsigned long long)chunks, p.err, p.timeout_ns);
             }
-            cons_bar();
+            tail_bar();                                     // + the helper warp: sGu (and the prefetched operands) are ready
+            BLK_STAMP(i, 3);
             BlkGram<K> gram;
             double vb = 0.0;
-            int sub = 0;
-            const int nsub = (rows + kBlkTile - 1) / kBlkTile;
-            for (int r0 = 0; r0 < rows; r0 += kBlkTile, ++sub) {
-                const int nr = min(kBlkTile, rows - r0);
+            const int tile = pre2 ? kBlkPre : kBlkTile;
+            double* aT = pre2 ? pT : sT;
+            double* aS = pre2 ? pS : sS;
+            double* aO = pre2 ? pO : sO;
+            for (int r0 = 0; r0 < rows; r0 += tile) {
+                const int nr = min(tile, rows - r0);
                 const int n_el = nr * K;
                 const int64_t base = (tl.c0 + rb + r0) * K;
-                for (int e = t; e < n_el; e += 256) sO[e] = __ldcg(Vold + base + e);
-                epi_stage_sums(sS, p.Bpart + base, n_el, chunks, cols * K);                      // local X^T U  (:424)
-                cons_bar();
+                if (!pre2)
+                    for (int e = t; e < n_el; e += 256) aO[e] = __ldcg(Vold + base + e);
+                epi_stage_sums(aS, p.Bpart + base, n_el, chunks, cols * K);                      // local X^T U  (:424)
                 if (p.nranks > 1) {
-                    // push this rank's sums of the sub-tile into every rank's receive slot, flag, wait for all, add in order
-                    const unsigned long long fs = (xs - 1) * (unsigned long long)nsub + sub + 1;   // per-CTA flag sequence
+                    // sum over ranks: every thread pushes the entries it owns into every rank's receive slot and then polls
+                    // the same entries of all ranks in its own buffer, adding them in rank order (bitwise identical everywhere)
                     for (int e = t; e < n_el; e += 256) {
-                        const double v = sS[e];
-                        for (int r = 0; r < p.nranks; ++r) p.xbuf[r][(xpar + p.rank) * p.xcount + base + e] = v;
+                        const double v = aS[e];
+                        for (int r = 0; r < p.nranks; ++r) ll_store(p.xbuf[r] + (xpar + p.rank) * p.xcount + base + e, v, xs);
                     }
-                    __threadfence_system();
-                    cons_bar();
-                    if (t < p.nranks) {
-                        st_release_sys_u64(p.xflag[t] + (size_t)p.rank * (tiles2 + 1) + b, fs);
-                        blk_wait_ge<true>(p.xflag[p.rank] + (size_t)t * (tiles2 + 1) + b, fs, p.err, p.timeout_ns);
-                    }
-                    cons_bar();
                     for (int e = t; e < n_el; e += 256) {
-                        double s = 0.0;
-                        for (int r = 0; r < p.nranks; ++r) s += __ldcg(p.xbuf[p.rank] + (xpar + r) * p.xcount + base + e);
-                        sS[e] = s;
+                        double sum = 0.0;
+                        for (int r = 0; r < p.nranks; ++r)
+                            sum += ll_wait(p.xbuf[p.rank] + (xpar + r) * p.xcount + base + e, xs, p.err, p.timeout_ns);
+                        aS[e] = sum;
                     }
-                    cons_bar();
+                    BLK_STAMP(i, 4);
                 }
+                cons_bar();
                 for (int e = t; e < n_el; e += 256) {
                     const int r = e / K, c = e - r * K;
                     const int64_t j = tl.c0 + rb + r0 + r;
-                    const double* vrow = sO + r * K;
-                    const double bb = sS[e];
+                    const double* vrow = aO + r * K;
+                    const double bb = aS[e];
                     double cden = 0.0;
 #pragma unroll
-                    for (int l = 0; l < K; ++l) cden = fma(vrow[l], sG[l * K + c], cden);       // V.Gu   (:425)
+                    for (int l = 0; l < K; ++l) cden = fma(vrow[l], sGu[l * K + c], cden);      // V.Gu   (:425)
                     const double v = vrow[c];
                     double num = bb, den = cden;
-                    const int32_t pr = p.pos[j * K + c];
+                    int32_t pr = -1;
+                    double wv = 0.0, dg = 0.0;
+                    if (pre2) {
+                        dg = pDg[e];
+                        if (dg >= 0.0) { pr = p.pos[j * K + c]; wv = pWv[e]; }
+                    } else {
+                        pr = p.pos[j * K + c];
+                        if (pr >= 0) {
+                            const Pathways& pw = p.pw;
+                            const int64_t pbase = pw.path_ptr[p.active[c]];
+                            for (int64_t e2 = pw.row_ptr[pr]; e2 < pw.row_ptr[pr + 1]; ++e2)
+                                wv = fma(pw.w[e2], __ldcg(Vold + (int64_t)pw.support_idx[pbase + pw.col_local[e2]] * K + c), wv);
+                            dg = pw.deg[pr];
+                        }
+                    }
                     if (pr >= 0) {
-                        const Pathways& pw = p.pw;
-                        const int64_t pbase = pw.path_ptr[p.active[c]];
-                        double wv = 0.0;
-                        for (int64_t e2 = pw.row_ptr[pr]; e2 < pw.row_ptr[pr + 1]; ++e2)
-                            wv = fma(pw.w[e2], __ldcg(Vold + (int64_t)pw.support_idx[pbase + pw.col_local[e2]] * K + c), wv);   // rows other CTAs wrote in this launch: L2
                         const double vp1 = v + 1.0;
                         const double man = gamma * wv;                                           // :434
                         const double ign = delta * (1.0 / (vp1 * vp1));                          // :438
                         num = bb + (man + ign);                                                  // :440
-                        den = cden + gamma * (pw.deg[pr] * v);                                   // :435,:441
-                        // (hist_vh below)
+                        den = cden + gamma * (dg * v);                                           // :435,:441
                     }
                     if (den < kEps) den = kEps;                                                  // :442
                     double vn = v * (num / den);                                                 // :443
                     if (vn < kEps) vn = kEps;                                                    // :444
-                    sT[e] = vn;
+                    aT[e] = vn;
                     Vnew[j * K + c] = vn;
                     if (pr >= 0) p.hist_vh[(size_t)step * kVhCap + p.doff[c] + (pr - p.pw.path_ptr[p.active[c]])] = vn;
                     vb = fma(vn, bb, vb);
                 }
                 cons_bar();
-                gram.add(sT, nr);
+                // the share of V_new (and its active-set values) is stored: release the W rows of the next pass 1
+                if (r0 + tile >= rows && t == 0) red_release_add(p.vdone, 1ull);
+                gram.add(aT, nr);
                 cons_bar();
             }
+            if (rows == 0 && t == 0) red_release_add(p.vdone, 1ull);
+            BLK_STAMP(i, 5);
             // sum(V_new * B) of this share: warp sums, then the 8 warp sums in order
             vb = warp_sum(vb);
             if ((t & 31) == 0) sW8[t >> 5] = vb;
@@ -562,25 +707,23 @@ block_kernel(const BlockParams p) {
                 for (int w = 0; w < 8; ++w) s += sW8[w];
                 p.vb2[me] = s;
             }
-            gram.finish(sBuf, p.part2 + me * K * K);
-            __threadfence();
+            gram.finish(sBuf, p.part2 + me * KK);
             cons_bar();
             if (t == 0) {
-                const unsigned long long prev = atomicAdd(p.done2 + tl.panel, 1ull);
+                const unsigned long long prev = atom_acq_rel_add(p.done2 + tl.panel, 1ull);
                 s_last = prev + 1ull == n2 * (unsigned long long)chunks;
             }
             cons_bar();
             if (s_last) {
-                __threadfence();
-                if (t < K * K)
-                    p.hist_Gvp[((size_t)step * p.panels2 + tl.panel) * K * K + t] =
-                        sum_strided_cg(p.part2 + (int64_t)tl.panel * chunks * K * K + t, chunks, K * K);
+                if (t < KK)
+                    p.hist_Gvp[((size_t)step * p.panels2 + tl.panel) * KK + t] =
+                        sum_strided_cg(p.part2 + (int64_t)tl.panel * chunks * KK + t, chunks, KK);
                 if (t == 128) p.hist_VBp[(size_t)step * p.panels2 + tl.panel] = sum_strided_cg(p.vb2 + (int64_t)tl.panel * chunks, chunks, 1);
-                __threadfence();
                 cons_bar();
-                if (t == 0) atomicAdd(p.vdone, 1ull);
+                if (t == 0) red_release_add(p.vfold, 1ull);
             }
             cons_bar();
+            BLK_STAMP(i, 6);
         }
     }
 }

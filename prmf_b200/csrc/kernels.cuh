@@ -125,7 +125,7 @@ __device__ __forceinline__ void block_sum_multi(double (&v)[NV], double* scratch
 // ----------------------------------------------------------------------------------------------------
 // ||X||_F^2  (np.linalg.norm(X), :640) : per-block partials, summed in order by sum_partials_kernel
 // ----------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sumsq_kernel(const double* __restrict__ X, int64_t ldx, int64_t m,
+static __global__ void __launch_bounds__(256) sumsq_kernel(const double* __restrict__ X, int64_t ldx, int64_t m,
                                                     int n2, double* __restrict__ part) {
     __shared__ double scratch[32];
     double acc = 0.0;
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const double* __restrict__ X
     if (threadIdx.x == 0) part[blockIdx.x] = t;
 }
 
-__global__ void sum_partials_kernel(const double* __restrict__ part, int count, double* __restrict__ out) {
+static __global__ void sum_partials_kernel(const double* __restrict__ part, int count, double* __restrict__ out) {
     __shared__ double scratch[32];
     double a = 0.0;
     for (int i = threadIdx.x; i < count; i += blockDim.x) a += part[i];
@@ -1137,7 +1137,7 @@ skinny_tma_gen_kernel(const double* __restrict__ M, int64_t ldm, int64_t rows_to
 }
 
 // Xt[j][i] = X[i][j] : the factor of 2 in HBM capacity buys a coalesced, reduction-free pass 1.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 transpose_kernel(const double* __restrict__ X, int64_t ldx, int64_t m, int64_t n, double* __restrict__ Xt,
                  int64_t ldxt) {
     __shared__ double tile[32][33];
@@ -1160,7 +1160,7 @@ transpose_kernel(const double* __restrict__ X, int64_t ldx, int64_t m, int64_t n
 // Sum the per-chunk X^T U partials and per-block U^T U partials in a fixed order into the packed
 // buffer that is all-reduced over ranks:  red = [ B (n*k) | Gu (k*k) | sum(U^2) | pad ]
 // ----------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 reduce_pack_kernel(const double* __restrict__ Bpart, int chunks, int64_t nk, const double* __restrict__ Gu_part,
                    int gu_blocks, int k, double* __restrict__ red) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1176,7 +1176,7 @@ reduce_pack_kernel(const double* __restrict__ Bpart, int chunks, int64_t nk, con
 
 // pos[j*k + c] = packed row of gene j in the active pathway of factor c (or -1, preset by a memset), and
 // the flattened ActiveSet.  grid = (blocks, k); doff/eoff = per-factor offsets into the flat arrays.
-__global__ void build_active_kernel(Pathways pw, const int32_t* __restrict__ active, int k,
+static __global__ void build_active_kernel(Pathways pw, const int32_t* __restrict__ active, int k,
                                     const int64_t* __restrict__ doff, const int64_t* __restrict__ eoff,
                                     int32_t* __restrict__ pos, int32_t* __restrict__ diag_gene,
                                     int32_t* __restrict__ diag_factor, double* __restrict__ diag_coef,
@@ -1503,7 +1503,7 @@ v_update_objective_kernel(const double* __restrict__ Vold, double* __restrict__ 
 // CPT x CPT block of the Gram; column ownership is interleaved in pairs (columns 32 j + 2 tx, +1) so the shared-memory
 // reads of a warp are conflict-free 128-bit accesses.
 // ----------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 gram_reduce_kernel(const double* __restrict__ parts, int count, int kk2, double* __restrict__ out) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e < kk2) out[e] = sum_strided(parts + e, count, kk2);
@@ -1756,7 +1756,7 @@ v_update_tiled_kernel(const double* __restrict__ Vold, double* __restrict__ Vnew
 
 // manifold / ignore terms of the objective (:344-352) over the flattened active set, spread over the grid (large k:
 // k pathways x hundreds of entries are too many gathers for one block).  Per-block partials, fixed order.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 manifold_parts_kernel(const double* __restrict__ V, int k, const double* __restrict__ Gv, ActiveSet as,
                       double* __restrict__ man_part, double* __restrict__ ign_part) {
     __shared__ double scratch[32];
@@ -1780,7 +1780,7 @@ manifold_parts_kernel(const double* __restrict__ V, int k, const double* __restr
 
 // Objective of one inner step as its own one-block launch (large k: after gram_reduce_kernel folded the Gram
 // partials; Gu and Gv arrive as single k*k matrices, the sum(V_new*B) partials per V-update block).
-__global__ void __launch_bounds__(kTailThreads)
+static __global__ void __launch_bounds__(kTailThreads)
 objective_kernel(const double* __restrict__ V, int k, const double* __restrict__ Gu, const double* __restrict__ Gv_in,
                  const double* __restrict__ VB_part, int vb_parts, const double* __restrict__ man_part,
                  const double* __restrict__ ign_part, int mi_parts, const double* __restrict__ normX_sq,
@@ -1822,7 +1822,7 @@ objective_kernel(const double* __restrict__ V, int k, const double* __restrict__
 
 // Objective of one inner step from per-panel partials (fused-tail path, k <= 10: the V update ran inside the pass-2
 // kernel and left `vparts` partials of V_new^T V_new and sum(V_new*B); Gu arrives as `gu_parts` partials).
-__global__ void __launch_bounds__(kTailThreads)
+static __global__ void __launch_bounds__(kTailThreads)
 objective_parts_kernel(const double* __restrict__ V, int k, const double* __restrict__ Gu_part, int gu_parts,
                        const double* __restrict__ Gv_part, const double* __restrict__ VB_part, int vparts,
                        const double* __restrict__ normX_sq, ActiveSet as, double* __restrict__ Gv,
@@ -1844,7 +1844,7 @@ objective_parts_kernel(const double* __restrict__ V, int k, const double* __rest
 // the block from what that step's V update left behind (per-panel Gram and sum(V_new*B) partials, U^T U, the
 // active-set values of V_new), so a block of n steps costs ONE launch instead of n on the critical path.  The
 // last block publishes Gv_new.  Same arithmetic and summation orders as objective_parts_kernel.
-__global__ void __launch_bounds__(kTailThreads)
+static __global__ void __launch_bounds__(kTailThreads)
 objective_deferred_kernel(int k, const double* __restrict__ hist_Gu, const double* __restrict__ hist_Gvp,
                           const double* __restrict__ hist_VBp, int vparts, const double* __restrict__ hist_vh,
                           int vh_stride, const double* __restrict__ normX_sq, ActiveSet as, double* __restrict__ Gv,
@@ -1901,7 +1901,7 @@ gram_rows_kernel(const double* __restrict__ M, int64_t rows_total, int k, int ro
 }
 
 // G[e] = sum_b G_part[b][e]  (fixed order)
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 sum_gram_parts_kernel(const double* __restrict__ G_part, int blocks, int kk2, double* __restrict__ G) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e < kk2) {
@@ -2021,7 +2021,7 @@ scores_kernel(const double* __restrict__ V, int k, const double* __restrict__ Gv
 }
 
 // manifold / ignore terms of the objective (:344-352) for the current V, standalone (prmf_objective).
-__global__ void __launch_bounds__(1024)
+static __global__ void __launch_bounds__(1024)
 manifold_ignore_kernel(const double* __restrict__ V, int k, const double* __restrict__ Gv, ActiveSet as,
                        double* __restrict__ out2) {
     __shared__ double scratch[32];
@@ -2046,7 +2046,7 @@ manifold_ignore_kernel(const double* __restrict__ V, int k, const double* __rest
 // ----------------------------------------------------------------------------------------------------
 // Exact residual ||X - U V^T||_F^2 (verification only; one extra pass over X).  Warp per row.
 // ----------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 residual_kernel(const double* __restrict__ X, int64_t ldx, int64_t m, int n, const double* __restrict__ U,
                 const double* __restrict__ V, int k, double* __restrict__ part) {
     __shared__ double scratch[32];

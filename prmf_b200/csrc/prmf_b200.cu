@@ -20,7 +20,7 @@
 #include <vector>
 
 #include "kernels.cuh"
-#include "block.cuh"
+#include "block_params.h"
 #include "fused.cuh"
 #include "tf32.cuh"
 #include "nccl_dyn.h"
@@ -136,7 +136,8 @@ struct prmf_handle {
     // persistent step kernel (block.cuh): a whole block of inner steps per cooperative launch
     bool use_block = false;                   // this rank can take it (fused-tail geometry, deferred objective, smem fits)
     bool blk_xchg = false;                    // sharded: every rank takes it with the same geometry (prmf_p2p_finalize)
-    unsigned long long* blk_ctr = nullptr;    // arrive1 | done1 | arrive2 | done2 | udone | vdone
+    bool block_forced = false;                // PRMF_BLOCK=1: also on one GPU
+    unsigned long long* blk_ctr = nullptr;    // arrive1 | done1 | arrive2 | done2 | udone | vdone | ufold | vfold
     unsigned long long blk_n1 = 0, blk_n2 = 0, blk_xseq = 0;
     size_t blk_smem = 0;
     uint32_t blk_stage_bytes = 0;
@@ -145,7 +146,6 @@ struct prmf_handle {
     unsigned long long spin_timeout_ns = 10000000000ull;
     bool failed = false;                      // a launch failed or a device wait expired: no further steps
     double* xbuf = nullptr;                   // push-exchange receive buffer inside p2p_buf
-    unsigned long long* xflag = nullptr;
     size_t xcount = 0;
 
     // single-pass fused X kernel (opt-in: PRMF_FUSED=1)
@@ -787,18 +787,14 @@ int launch_scores(prmf_handle* h) {
     return launch_scores_t<16>(h);
 }
 
-// persistent step kernel: halves [h0, h0 + nh) of a block in one cooperative launch (block.cuh)
-template <int K>
-int launch_block_t(prmf_handle* h, const BlockParams& prm, int grid) {
-    CU(cudaFuncSetAttribute(block_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->blk_smem));
-    BlockParams copy = prm;
-    void* args[] = {(void*)&copy};
-    CU(cudaLaunchCooperativeKernel((const void*)block_kernel<K>, dim3((unsigned)grid), dim3(kTmaThreads), args, h->blk_smem,
-                                   h->stream));
-    return PRMF_OK;
+// persistent step kernel: halves [h0, h0 + nh) of a block in one cooperative launch (block.cuh / block.cu)
+// The persistent step kernel is the default for sharded runs (there the exchange lives inside it); on one GPU it
+// times like the two-launch path and draws more power in sustained runs, so it is opt-in there (PRMF_BLOCK=1).
+bool block_path(const prmf_handle* h) {
+    if (!h->use_block) return false;
+    if (h->comm == nullptr) return h->block_forced;
+    return h->blk_xchg;
 }
-
-bool block_path(const prmf_handle* h) { return h->use_block && (h->comm == nullptr || h->blk_xchg); }
 
 int launch_block(prmf_handle* h, int h0, int nh) {
     if (nh <= 0) return PRMF_OK;
@@ -818,9 +814,10 @@ int launch_block(prmf_handle* h, int h0, int nh) {
     prm.done1 = c; c += h->tpanels1;
     prm.arrive2 = c; c += h->tpanels;
     prm.done2 = c; c += h->tpanels;
-    prm.udone = c; prm.vdone = c + 1;
+    prm.udone = c; prm.vdone = c + 1; prm.ufold = c + 2; prm.vfold = c + 3;
     prm.base1 = h->blk_n1; prm.base2 = h->blk_n2;
     prm.h0 = h0; prm.nh = nh;
+    { const char* ef = getenv("PRMF_BLOCK_FLAGS"); prm.flags = ef ? (unsigned int)atoi(ef) : 0u; }
     prm.pw = h->pw; prm.active = h->active; prm.pos = h->pos; prm.gd = h->gd;
     prm.hist_Gu = h->hist_Gu; prm.hist_Gvp = h->hist_Gvp; prm.hist_VBp = h->hist_VBp; prm.hist_vh = h->hist_vh;
     prm.doff = h->as_off;
@@ -828,25 +825,20 @@ int launch_block(prmf_handle* h, int h0, int nh) {
     prm.nranks = h->comm ? h->nranks : 1; prm.rank = h->rank;
     if (prm.nranks > 1) {
         const size_t off_buf = (size_t)(h->xbuf - h->p2p_buf);                 // same layout in every rank's buffer
-        const size_t off_flag = (size_t)((double*)h->xflag - h->p2p_buf);
-        for (int r = 0; r < h->nranks; ++r) {
-            prm.xbuf[r] = (double*)h->peer_base[r] + off_buf;
-            prm.xflag[r] = (unsigned long long*)((double*)h->peer_base[r] + off_flag);
-        }
+        for (int r = 0; r < h->nranks; ++r) prm.xbuf[r] = (ulonglong2*)((double*)h->peer_base[r] + off_buf);
         prm.xcount = h->xcount;
         prm.xbase = h->blk_xseq;
     }
     int n_p1 = 0, n_p2 = 0;
     for (int i = 0; i < nh; ++i) (((h0 + i) & 1) == 0 ? n_p1 : n_p2)++;
     const int grid = std::max(h->tpanels1 * h->tchunks1, h->tpanels * h->tchunks);
-    int rc = 0;
-    KT_SWITCH_RC(h->k, rc, launch_block_t, h, prm, grid);
-    if (!rc) {
-        h->launches++;
-        cudaError_t e_ = cudaGetLastError();
-        if (e_ != cudaSuccess) rc = fail(h, PRMF_ERR_CUDA, "launch of block_kernel failed: %s", cudaGetErrorString(e_));
+    cudaError_t e_ = prmf_launch_block_kernel(h->k, prm, grid, h->blk_smem, h->stream);
+    if (e_ == cudaSuccess) e_ = cudaGetLastError();
+    if (e_ != cudaSuccess) {                      // the counters below only move for a launch that is really queued
+        h->failed = true;
+        return fail(h, PRMF_ERR_CUDA, "launch of block_kernel failed: %s", cudaGetErrorString(e_));
     }
-    if (rc) { h->failed = true; return rc; }      // the counters below only move for a launch that is really queued
+    h->launches++;
     h->blk_n1 += n_p1; h->blk_n2 += n_p2;
     if (prm.nranks > 1) h->blk_xseq += n_p2;
     if (n_p1 & 1) std::swap(h->U, h->U2);
@@ -1302,7 +1294,9 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
             *panel_w = (int)round_up((std::max<int64_t>(1, cols) + *panels - 1) / *panels, 4);
             *chunks = std::max(1, h->sm_count / *panels);
             *chunks = (int)std::min<int64_t>(*chunks, std::max<int64_t>(1, rows / (4 * h->tma_rs)));
-            *rpc = round_up(std::max<int64_t>(1, (rows + *chunks - 1) / *chunks), h->tma_rs);
+            // rows per chunk: even (the W rows of a chunk must start 16-byte aligned for the bulk copies), not a multiple
+            // of the stage height -- a ragged last stage costs less than a last chunk that is nearly empty
+            *rpc = round_up(std::max<int64_t>(1, (rows + *chunks - 1) / *chunks), 2);
             const size_t xb = (size_t)h->tma_rs * *panel_w * 8;
             const size_t wb = (((size_t)h->tma_rs * k + 16) * 8 + 127) & ~(size_t)127;
             *smem = h->tma_stages * (xb + wb) + 2 * h->tma_stages * sizeof(uint64_t);
@@ -1376,7 +1370,7 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
         total += pad(128, d) + 4 * pad(kk2, d) + pad((size_t)gu_parts_max * kk2, d) + pad((size_t)gv_parts_max * kk2, d);
         total += pad(gv_parts_max, d) + pad((size_t)std::max({h->chunks, h->tchunks, h->fp.groups, h->tc_chunks2}) * nk, d);   // VB_part, Bpart
         total += pad(2 * ((size_t)h->tpanels1 + h->tpanels) + 2, sizeof(unsigned long long));     // fused-tail counters
-        total += pad(2 * ((size_t)h->tpanels1 + h->tpanels) + 2, sizeof(unsigned long long)) + pad(1, sizeof(unsigned int));   // block kernel
+        total += pad(2 * ((size_t)h->tpanels1 + h->tpanels) + 4, sizeof(unsigned long long)) + pad(1, sizeof(unsigned int));   // block kernel
         total += pad((size_t)std::max(h->tpanels1 * h->tchunks1, h->tpanels * h->tchunks) * kk2, d) +
                  pad((size_t)h->tpanels * h->tchunks, d);                                          // per-CTA partials
         total += pad((size_t)nk + kk2 + 2, d) + pad(1, d) + pad((size_t)h->sm_count * 8, d) + pad(2, d);
@@ -1410,7 +1404,7 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
     TAKE(h->Gv_part, double, (size_t)gv_parts_max * kk2);
     TAKE(h->VB_part, double, gv_parts_max);
     TAKE(h->epi_counters, unsigned long long, 2 * ((size_t)h->tpanels1 + h->tpanels) + 2);
-    TAKE(h->blk_ctr, unsigned long long, 2 * ((size_t)h->tpanels1 + h->tpanels) + 2);
+    TAKE(h->blk_ctr, unsigned long long, 2 * ((size_t)h->tpanels1 + h->tpanels) + 4);
     TAKE(h->err_word, unsigned int, 1);
     TAKE(h->epi_part2, double, (size_t)std::max(h->tpanels1 * h->tchunks1, h->tpanels * h->tchunks) * kk2);
     TAKE(h->epi_vb2, double, (size_t)h->tpanels * h->tchunks);
@@ -1436,7 +1430,7 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
         if (h->Xt) cudaMemsetAsync(h->Xt, 0, sizeof(double) * n * h->ldxt, h->stream);
         cudaMemsetAsync(h->ticket, 0, sizeof(unsigned int), h->stream);
         cudaMemsetAsync(h->epi_counters, 0, sizeof(unsigned long long) * (2 * ((size_t)h->tpanels1 + h->tpanels) + 2), h->stream);
-        cudaMemsetAsync(h->blk_ctr, 0, sizeof(unsigned long long) * (2 * ((size_t)h->tpanels1 + h->tpanels) + 2), h->stream);
+        cudaMemsetAsync(h->blk_ctr, 0, sizeof(unsigned long long) * (2 * ((size_t)h->tpanels1 + h->tpanels) + 4), h->stream);
         cudaMemsetAsync(h->err_word, 0, sizeof(unsigned int), h->stream);
         cudaMemsetAsync(h->U, 0, sizeof(double) * (m_local + pad_rows) * k, h->stream);
         cudaMemsetAsync(h->U2, 0, sizeof(double) * (m_local + pad_rows) * k, h->stream);
@@ -1475,8 +1469,9 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
         const size_t wb = ((size_t)kBlkRS * k * 8 + 127) & ~(size_t)127;
         h->blk_stage_bytes = (uint32_t)((size_t)kBlkRS * std::max(h->tpanel_w1, h->tpanel_w) * 8 + wb);
         h->blk_smem = (size_t)h->tma_stages * h->blk_stage_bytes + 2 * h->tma_stages * sizeof(uint64_t) +
-                      sizeof(double) * (128 + 8 * (size_t)k * k + 3 * (size_t)kBlkTile * k);
+                      sizeof(double) * (256 + 8 * (size_t)k * k + (size_t)kBlkRowsCap * k);
         h->use_block = h->use_epi && h->defer_ok && !(eb && atoi(eb) == 0) && h->blk_smem <= 227 * 1024;
+        h->block_forced = eb && atoi(eb) == 1;
         if (cudaHostAlloc((void**)&h->err_host, sizeof(unsigned int), cudaHostAllocDefault) == cudaSuccess) *h->err_host = 0;
         else h->err_host = nullptr;
     }
@@ -1913,14 +1908,12 @@ int prmf_p2p_export(prmf_handle* h, uint8_t* handle_out) {
         const size_t old_total = 2 * h->p2p_red_count + 64 + (size_t)kMaxPeers * (h->sm_count + 2);   // + per-CTA flags
         // push exchange of the persistent step kernel: receive slots [parity][source rank][n*k + k*k] + its flags
         h->xcount = h->p2p_red_count;
-        const size_t xdoubles = 2 * (size_t)kMaxPeers * h->xcount;
-        const size_t xflags = (size_t)kMaxPeers * (h->sm_count + 2);
-        const size_t total = old_total + xdoubles + xflags;
+        const size_t xdoubles = 2 * 2 * (size_t)kMaxPeers * h->xcount;        // 16-byte {value, sequence} entries
+        const size_t total = ((old_total + 1) & ~(size_t)1) + xdoubles;
         int rc = dalloc(h, &h->p2p_buf, total);
         if (rc) return rc;
         CU(cudaMemset(h->p2p_buf, 0, total * sizeof(double)));
-        h->xbuf = h->p2p_buf + old_total;
-        h->xflag = (unsigned long long*)(h->xbuf + xdoubles);
+        h->xbuf = h->p2p_buf + ((old_total + 1) & ~(size_t)1);                // 16-byte aligned
     }
     cudaIpcMemHandle_t hd;
     CU(cudaIpcGetMemHandle(&hd, h->p2p_buf));
@@ -1972,7 +1965,7 @@ int prmf_p2p_finalize(prmf_handle* h) {
     CU(cudaStreamSynchronize(h->stream));
     h->use_xchg = sum[0] > h->nranks - 0.5;
     const bool same_chunks = std::fabs(h->nranks * sum[3] - sum[2] * sum[2]) < 0.5;
-    h->blk_xchg = !h->use_xchg && sum[1] > h->nranks - 0.5 && same_chunks && h->tpanels * h->tchunks + 1 <= h->sm_count + 2;
+    h->blk_xchg = !h->use_xchg && sum[1] > h->nranks - 0.5 && same_chunks;
     return PRMF_OK;
 }
 

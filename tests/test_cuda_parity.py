@@ -18,6 +18,15 @@ def test_whole_loop_matches_reference_fixture(case):
     check_run_against_golden(g, U, V, od, trace)
 
 
+@pytest.mark.parametrize("case", ["test1_norm", "test2_raw", "small_planted"])
+def test_whole_loop_persistent_kernel_matches_reference_fixture(monkeypatch, case):
+    """The persistent step kernel (the default of sharded runs; PRMF_BLOCK=1 selects it on one GPU) on the fixtures."""
+    monkeypatch.setenv("PRMF_BLOCK", "1")
+    g = load_golden(case)
+    U, V, od, trace, _ = run_product(g)
+    check_run_against_golden(g, U, V, od, trace)
+
+
 def _instance(m, n, k, P, seed, weighted=False, psize=12):
     from prmf_b200 import synth
     X, nodelist, Gs = synth.small_instance(m=m, n=n, k_true=min(3, P), n_pathways=P, pathway_size=psize,
@@ -266,12 +275,12 @@ def test_speculative_pass_is_bitwise_neutral(k):
 
 
 # ---- the launch-structure switches must not change results ----------------------------------------------
-@pytest.mark.parametrize("env", [{"PRMF_EPI": "0"}, {"PRMF_BLOCK": "0"}, {"PRMF_TMA": "0"}])
+@pytest.mark.parametrize("env", [{"PRMF_EPI": "0"}, {"PRMF_BLOCK": "1"}, {"PRMF_TMA": "0"}])
 @pytest.mark.parametrize("m,n,k,P", [(200, 517, 10, 12), (1000, 6750, 10, 20), (37, 131, 3, 5)])
 def test_launch_structure_switches(monkeypatch, env, m, n, k, P):
     """PRMF_EPI=0: separate U / V-update launches instead of the fused tails (the path of ranks without rows);
-    PRMF_BLOCK=0: two fused-tail launches per inner step instead of the persistent step kernel; PRMF_TMA=0: the
-    pre-TMA X-stream kernel."""
+    PRMF_BLOCK=1: the persistent step kernel (the default of sharded runs) on one GPU instead of two fused-tail launches
+    per inner step; PRMF_TMA=0: the pre-TMA X-stream kernel."""
     from prmf_b200 import nmf_manifold_vec_update
     for key, val in env.items():
         monkeypatch.setenv(key, val)
@@ -365,7 +374,7 @@ def test_score_tables_large_and_small_pathways():
 # ---- the persistent step kernel (block.cuh) -------------------------------------------------------------
 @pytest.mark.parametrize("m,n,k,P", [(300, 1200, 6, 9), (1500, 2100, 10, 12), (37, 131, 3, 5), (700, 523, 10, 9)])
 def test_persistent_step_kernel_matches_two_launch_path(monkeypatch, m, n, k, P):
-    """One cooperative launch per block of steps (default) against the two-launches-per-step path (PRMF_BLOCK=0) over
+    """One cooperative launch per block of steps (PRMF_BLOCK=1; the default of sharded runs) against the two-launches-per-step path over
     three blocks with the speculative pass on: same objective parts, score tables, U and V to rounding (the two
     differ only in the order the U^T U partials of a share are added)."""
     from prmf_b200 import CudaEngine, pack_pathways
@@ -391,9 +400,10 @@ def test_persistent_step_kernel_matches_two_launch_path(monkeypatch, m, n, k, P)
             np.testing.assert_allclose(u, v, rtol=1e-11, atol=1e-13)
 
 
-def test_persistent_step_kernel_against_oracle_many_steps():
+def test_persistent_step_kernel_against_oracle_many_steps(monkeypatch):
     """Ten steps in one launch against the oracle (every step's objective parts)."""
     from prmf_b200 import CudaEngine, pack_pathways
+    monkeypatch.setenv("PRMF_BLOCK", "1")
     X, nodelist, Gs, U, V, active = _instance(900, 1300, 10, 14, seed=77, weighted=True)
     Uo, Vo, parts_o, _, _, _ = oracle_block(X, U, V, Gs, nodelist, active, 10, 1.7, 0.6)
     with CudaEngine(900, 900, 1300, 10) as eng:
@@ -413,6 +423,7 @@ def test_bounded_wait_returns_timeout_instead_of_hanging(monkeypatch):
     from prmf_b200 import CudaEngine, pack_pathways
     from prmf_b200._lib import PrmfLibraryError
     monkeypatch.setenv("PRMF_SPIN_TIMEOUT_MS", "200")
+    monkeypatch.setenv("PRMF_BLOCK", "1")
     X, nodelist, Gs, U, V, active = _instance(300, 600, 6, 5, seed=4)
     with CudaEngine(300, 300, 600, 6) as eng:
         eng.set_X(X); eng.set_pathways(pack_pathways(Gs, nodelist)); eng.set_UV(U, V); eng.set_active(active)

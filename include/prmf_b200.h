@@ -181,6 +181,15 @@ int64_t prmf_launch_count(const prmf_handle* h);
 int prmf_kernel_times(prmf_handle* h, int reset, double* phase_ms, int64_t* phase_count);
 /* Enable (1) / disable (0) per-kernel event timing inside prmf_step (off by default). */
 int prmf_set_profiling(prmf_handle* h, int on);
+/* A_local (m_local x k, row-major, host) = X_local . V for the current V: the pass-1 X stream of the inner step
+ * (prmf_runner.py:420) on its own.  It is the dense product of the steps around the path as well: the ridge transfer
+ * of a fitted V to new samples (reference script/transfer_learning.R:108, B^T = Y^T Z (Z^T Z + l I)^-1) needs exactly
+ * Y^T Z.  Sharded handles return their own row block. */
+int prmf_project(prmf_handle* h, double* A_local);
+/* The library keeps the two large buffers of a destroyed handle (X and its transposed copy) for the next handle of the
+ * same shape on the same device (allocating and freeing multi-GB buffers dominates a short solve otherwise); at most
+ * 4 buffers / 24 GB are held.  PRMF_POOL=0 (environment) disables the cache; this call frees what is held. */
+int prmf_release_pool(void);
 /* Fault injection for the tests of the bounded device waits (a lost launch or a dead peer must come
  * back as an error code, not as a hang).  kind 1: the next persistent step launch waits for a thread-block arrival
  * that never happens; kind 2: it waits for a peer-exchange flag that never comes.  The waits expire after

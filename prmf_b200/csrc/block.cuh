@@ -86,6 +86,45 @@ __device__ __forceinline__ double ll_wait(const ulonglong2* src, unsigned long l
     return __longlong_as_double((long long)lo);
 }
 
+// Sum over ranks of one entry: the entries of ALL ranks are polled together (one round of local loads per sweep
+// instead of one dependent poll per rank), then added in rank order.  Kept small on purpose: the kernel's main loop
+// lives at the register limit of a 10-warp CTA (168 per thread); anything bigger here ends up as spills or register
+// moves inside the stream (and a non-inlined call costs even more: the ABI pins the allocation of the whole kernel).
+__device__ __forceinline__ double ll_gather(const ulonglong2* mine, size_t xpar, size_t xcount, int nranks, size_t idx,
+                                            unsigned long long seq, unsigned int* err, unsigned long long timeout_ns) {
+    double v[kMaxPeers];
+    unsigned int pend = (1u << nranks) - 1u;
+    unsigned long long t0 = 0;
+    unsigned int polls = 0;
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r) v[r] = 0.0;
+    while (pend) {
+        unsigned long long lo[kMaxPeers], hi[kMaxPeers];
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r) {
+            hi[r] = ~0ull;
+            lo[r] = 0ull;
+            if ((pend >> r) & 1u)
+                asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo[r]), "=l"(hi[r]) : "l"(mine + (xpar + r) * xcount + idx));
+        }
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r)
+            if (hi[r] == seq) { v[r] = __longlong_as_double((long long)lo[r]); pend &= ~(1u << r); }
+        if (pend) {
+            __nanosleep(20);
+            if ((++polls & 255u) == 0u) {
+                const unsigned long long now = blk_gtime();
+                if (t0 == 0) t0 = now;
+                if (now - t0 > timeout_ns || ld_volatile_u32(err) != 0u) { atomicOr(err, kErrTimeoutPeer); break; }
+            }
+        }
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r) sum += v[r];          // rank order; absent ranks contribute +0.0
+    return sum;
+}
+
 // per-thread running Gram accumulation over the sub-tiles of a share (thread = (pair a,b ; row slice))
 template <int K>
 struct BlkGram {
@@ -639,12 +678,8 @@ block_kernel(const BlockParams p) {
                         const double v = aS[e];
                         for (int r = 0; r < p.nranks; ++r) ll_store(p.xbuf[r] + (xpar + p.rank) * p.xcount + base + e, v, xs);
                     }
-                    for (int e = t; e < n_el; e += 256) {
-                        double sum = 0.0;
-                        for (int r = 0; r < p.nranks; ++r)
-                            sum += ll_wait(p.xbuf[p.rank] + (xpar + r) * p.xcount + base + e, xs, p.err, p.timeout_ns);
-                        aS[e] = sum;
-                    }
+                    for (int e = t; e < n_el; e += 256)
+                        aS[e] = ll_gather(p.xbuf[p.rank], xpar, p.xcount, p.nranks, (size_t)(base + e), xs, p.err, p.timeout_ns);
                     BLK_STAMP(i, 4);
                 }
                 cons_bar();

@@ -1174,6 +1174,13 @@ reduce_pack_kernel(const double* __restrict__ Bpart, int chunks, int64_t nk, con
     }
 }
 
+// out[e] = fixed-order sum of `chunks` partials (prmf_project: A = X.V from the pass-1 partials)
+static __global__ void __launch_bounds__(256)
+sum_chunks_kernel(const double* __restrict__ part, int chunks, int64_t count, double* __restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < count) out[idx] = sum_strided(part + idx, chunks, count);
+}
+
 // pos[j*k + c] = packed row of gene j in the active pathway of factor c (or -1, preset by a memset), and
 // the flattened ActiveSet.  grid = (blocks, k); doff/eoff = per-factor offsets into the flat arrays.
 static __global__ void build_active_kernel(Pathways pw, const int32_t* __restrict__ active, int k,

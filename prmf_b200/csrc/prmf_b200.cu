@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -36,6 +37,46 @@ struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
 };
+
+// Cache of the large per-handle device buffers (X and its transposed copy) across handles of one process:
+// cudaMalloc / cudaFree of multi-GB buffers cost from a few ms to a second each on these boxes, which is most of the
+// wall time of a short solve that creates and destroys a handle (random restarts, repeated solves of one instance).
+// A freed buffer is kept (bounded count and bytes) and handed to the next handle that asks for the same size on the
+// same device.  PRMF_POOL=0 disables it; prmf_release_pool() returns everything to the driver.
+struct BigPool {
+    struct Ent { void* p; size_t bytes; int device; };
+    std::vector<Ent> free_list;
+    size_t held = 0;
+    static constexpr size_t kMaxEntries = 4;
+    static constexpr size_t kMaxBytes = (size_t)24 << 30;
+    bool enabled() const { const char* e = getenv("PRMF_POOL"); return !(e && atoi(e) == 0); }
+    cudaError_t alloc(void** out, size_t bytes, int device) {
+        if (enabled())
+            for (size_t i = 0; i < free_list.size(); ++i)
+                if (free_list[i].bytes == bytes && free_list[i].device == device) {
+                    *out = free_list[i].p;
+                    held -= bytes;
+                    free_list.erase(free_list.begin() + i);
+                    return cudaSuccess;
+                }
+        return cudaMalloc(out, bytes);
+    }
+    void release(void* p, size_t bytes, int device) {
+        if (!p) return;
+        if (enabled() && free_list.size() < kMaxEntries && held + bytes <= kMaxBytes) {
+            free_list.push_back({p, bytes, device});
+            held += bytes;
+            return;
+        }
+        cudaFree(p);
+    }
+    void drain() {
+        for (auto& e : free_list) { cudaSetDevice(e.device); cudaFree(e.p); }
+        free_list.clear();
+        held = 0;
+    }
+};
+BigPool g_pool;
 
 }  // namespace
 
@@ -613,6 +654,26 @@ int recompute_Gv(prmf_handle* h) {
     return PRMF_OK;
 }
 
+// device arrays of the flattened active set (ActiveSet): capacity in diagonal / off-diagonal entries
+int alloc_active_arena(prmf_handle* h, int64_t cap_diag, int64_t cap_off) {
+    const int k = h->k;
+    CU(cudaStreamSynchronize(h->stream));
+    h->as_arena.release();
+    h->as_cap_diag = cap_diag;
+    h->as_cap_off = cap_off;
+    const size_t n_i32 = (size_t)(2 * h->as_cap_diag + 5 * h->as_cap_off);
+    const size_t n_f64 = (size_t)(h->as_cap_diag + h->as_cap_off);
+    const size_t total = ((n_i32 * 4 + 255) & ~(size_t)255) + ((n_f64 * 8 + 255) & ~(size_t)255) +
+                         ((sizeof(int64_t) * 2 * (k + 1) + 255) & ~(size_t)255);
+    cudaError_t ea = cudaMalloc((void**)&h->as_arena.base, total);
+    if (ea != cudaSuccess) return fail(h, PRMF_ERR_NOMEM, "cudaMalloc active set: %s", cudaGetErrorString(ea));
+    h->as_arena.cap = total;
+    h->as_f64 = h->as_arena.take<double>(n_f64);
+    h->as_i32 = h->as_arena.take<int32_t>(n_i32);
+    h->as_off = h->as_arena.take<int64_t>((size_t)2 * (k + 1));
+    return PRMF_OK;
+}
+
 int ensure_pos(prmf_handle* h) {
     if (!h->pos_dirty) return PRMF_OK;
     const int k = h->k;
@@ -625,21 +686,9 @@ int ensure_pos(prmf_handle* h) {
         offs[k + 1 + c + 1] = offs[k + 1 + c] + (h->row_ptr_host[end] - h->row_ptr_host[beg]);
     }
     const int64_t nd = offs[k], no = offs[2 * k + 1];
-    if (nd > h->as_cap_diag || no > h->as_cap_off || !h->as_i32) {
-        CU(cudaStreamSynchronize(h->stream));
-        h->as_arena.release();
-        h->as_cap_diag = std::max<int64_t>(nd * 2, 1024);
-        h->as_cap_off = std::max<int64_t>(no * 2, 4096);
-        const size_t n_i32 = (size_t)(2 * h->as_cap_diag + 5 * h->as_cap_off);
-        const size_t n_f64 = (size_t)(h->as_cap_diag + h->as_cap_off);
-        const size_t total = ((n_i32 * 4 + 255) & ~(size_t)255) + ((n_f64 * 8 + 255) & ~(size_t)255) +
-                             ((sizeof(int64_t) * 2 * (k + 1) + 255) & ~(size_t)255);
-        cudaError_t ea = cudaMalloc((void**)&h->as_arena.base, total);
-        if (ea != cudaSuccess) return fail(h, PRMF_ERR_NOMEM, "cudaMalloc active set: %s", cudaGetErrorString(ea));
-        h->as_arena.cap = total;
-        h->as_f64 = h->as_arena.take<double>(n_f64);
-        h->as_i32 = h->as_arena.take<int32_t>(n_i32);
-        h->as_off = h->as_arena.take<int64_t>((size_t)2 * (k + 1));
+    if (nd > h->as_cap_diag || no > h->as_cap_off || !h->as_i32) {     // (prmf_set_pathways sizes it for the k largest pathways)
+        int rc = alloc_active_arena(h, std::max<int64_t>(nd * 2, 1024), std::max<int64_t>(no * 2, 4096));
+        if (rc) return rc;
     }
     int32_t* dg = h->as_i32;
     int32_t* df = dg + h->as_cap_diag;
@@ -1382,15 +1431,22 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
     }
 #define ALLOC(ptr, count) if (!rc) rc = dalloc(h, &ptr, (size_t)(count))
 #define TAKE(ptr, T, count) if (!rc) { ptr = h->arena.take<T>((size_t)(count)); if (!ptr) rc = fail(h, PRMF_ERR_NOMEM, "arena exhausted"); }
+#define ALLOC_BIG(ptr, T, count)                                                                                   \
+    if (!rc) {                                                                                                       \
+        const size_t bytes_ = sizeof(T) * (size_t)(count);                                                           \
+        cudaError_t eb_ = g_pool.alloc((void**)&ptr, bytes_, device);                                                \
+        if (eb_ != cudaSuccess) { ptr = nullptr; rc = fail(h, PRMF_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes_, cudaGetErrorString(eb_)); } \
+    }
     if (h->x_tf32) {
-        ALLOC(h->X32, (size_t)std::max<int64_t>(1, m_local) * h->ldx32);
-        ALLOC(h->Xt32, (size_t)n * h->ldxt32);
+        ALLOC_BIG(h->X32, float, (size_t)std::max<int64_t>(1, m_local) * h->ldx32);
+        ALLOC_BIG(h->Xt32, float, (size_t)n * h->ldxt32);
         ALLOC(h->Vt32, (size_t)h->Kp * h->ldx32);
         ALLOC(h->Ut32, (size_t)h->Kp * h->ldxt32);
     } else {
-        ALLOC(h->X, (size_t)std::max<int64_t>(1, m_local) * h->ldx);
-        ALLOC(h->Xt, (size_t)n * h->ldxt);
+        ALLOC_BIG(h->X, double, (size_t)std::max<int64_t>(1, m_local) * h->ldx);
+        ALLOC_BIG(h->Xt, double, (size_t)n * h->ldxt);
     }
+#undef ALLOC_BIG
     TAKE(h->U, double, (m_local + pad_rows) * k);
     TAKE(h->Ub, double, (m_local + pad_rows) * k);
     TAKE(h->U2, double, (m_local + pad_rows) * k);
@@ -1515,11 +1571,11 @@ int prmf_destroy(prmf_handle* h) {
     if (h->err_host) cudaFreeHost(h->err_host);
     if (h->p2p_buf) cudaFree(h->p2p_buf);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-    if (h->X) cudaFree(h->X);
-    if (h->Xt) cudaFree(h->Xt);
+    g_pool.release(h->X, sizeof(double) * (size_t)std::max<int64_t>(1, h->m) * h->ldx, h->device);
+    g_pool.release(h->Xt, sizeof(double) * (size_t)h->n * h->ldxt, h->device);
     if (h->hist) cudaFree(h->hist);
-    if (h->X32) cudaFree(h->X32);
-    if (h->Xt32) cudaFree(h->Xt32);
+    g_pool.release(h->X32, sizeof(float) * (size_t)std::max<int64_t>(1, h->m) * h->ldx32, h->device);
+    g_pool.release(h->Xt32, sizeof(float) * (size_t)h->n * h->ldxt32, h->device);
     if (h->Vt32) cudaFree(h->Vt32);
     if (h->Ut32) cudaFree(h->Ut32);
     h->arena.release();
@@ -1662,6 +1718,14 @@ int prmf_set_pathways(prmf_handle* h, int32_t P, const int64_t* path_ptr, const 
     h->have_pw = true;
     h->have_active = false;
     h->pos_dirty = true;
+    {   // every factor may pick the largest pathway: size the active-set arrays for that now, not in the middle of a block
+        const int64_t nd = std::max<int64_t>((int64_t)h->k * h->max_support, 1024);
+        const int64_t no = std::max<int64_t>((int64_t)h->k * h->max_edges, 4096);
+        if (nd > h->as_cap_diag || no > h->as_cap_off || !h->as_i32) {
+            int rc2 = alloc_active_arena(h, nd, no);
+            if (rc2) return rc2;
+        }
+    }
     return PRMF_OK;
 }
 
@@ -1991,6 +2055,29 @@ int prmf_kernel_times(prmf_handle* h, int reset, double* phase_ms, int64_t* phas
         if (phase_count) phase_count[i] = h->phase_n[i];
         if (reset) { h->phase_ms[i] = 0; h->phase_n[i] = 0; }
     }
+    return PRMF_OK;
+}
+
+int prmf_project(prmf_handle* h, double* A_local) {
+    if (!h || (!A_local && h->m > 0)) return PRMF_ERR_ARG;
+    if (!h->have_X || !h->have_UV) return fail(h, PRMF_ERR_STATE, "prmf_project needs X and V");
+    if (h->failed) return fail(h, PRMF_ERR_STATE, "the handle is in a failed state");
+    CU(cudaSetDevice(h->device));
+    if (h->m == 0) return PRMF_OK;
+    cancel_ahead(h);                                   // a speculative pass left other partials in Apart
+    int rc = launch_xv(h);                             // the pass-1 stream of the inner step, without its U update
+    if (rc) return rc;
+    const int64_t cnt = h->m * h->k;
+    double* dst = h->U2;                               // scratch: the second U buffer is free between steps
+    sum_chunks_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(h->Apart, a_chunks(h), cnt, dst);
+    LAUNCH_CHECK("sum_chunks_kernel");
+    CU(cudaMemcpyAsync(A_local, dst, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return PRMF_OK;
+}
+
+int prmf_release_pool(void) {
+    g_pool.drain();
     return PRMF_OK;
 }
 

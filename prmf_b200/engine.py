@@ -168,6 +168,12 @@ class CudaEngine:
                                          _ptr(tables[2]) if tables else None, 1 if prefetch else 0))
         return parts, float(gd[0]), float(gd[1]), tables
 
+    def project(self):
+        """X_local . V for the current V (m_local x k): the pass-1 stream on its own (prmf_project)."""
+        A = np.empty((self.m, self.k))
+        self._ck(self.lib.prmf_project(self.h, _ptr(A)))
+        return A
+
     def snapshot_best(self):
         self._ck(self.lib.prmf_snapshot_best(self.h))
 

@@ -43,35 +43,43 @@ def pack_pathways(Gs, nodelist):
     """
     index = {g: i for i, g in enumerate(nodelist)}
     n = len(nodelist)
-    path_ptr = [0]
-    row_ptr = [0]
-    supp_all, col_all, w_all = [], [], []
-    for G in Gs:
-        nodes = [g for g in G.nodes() if g in index]
-        local = {g: i for i, g in enumerate(nodes)}
-        gidx = np.fromiter((index[g] for g in nodes), dtype=np.int64, count=len(nodes))
-        rows, cols, vals = [], [], []
+    # one pass over the graphs collects flat edge lists (Python only touches every node and edge once); everything
+    # else -- mirroring, sorting rows by neighbour gene, row pointers -- is done for all pathways at once in numpy
+    P = len(Gs)
+    sizes = np.zeros(P, dtype=np.int64)
+    supp_all, e_path, e_a, e_b, e_w = [], [], [], [], []
+    get = index.get
+    for p, G in enumerate(Gs):
+        local = {}
+        for g in G.nodes():
+            i = get(g)
+            if i is not None:
+                local[g] = len(local)
+                supp_all.append(i)
+        sizes[p] = len(local)
+        lget = local.get
         for a, b, d in G.edges(data=True):
-            if a in local and b in local:
-                ww = d.get("weight", 1)
-                ia, ib = local[a], local[b]
-                rows.append(ia); cols.append(ib); vals.append(ww)
-                if ia != ib:
-                    rows.append(ib); cols.append(ia); vals.append(ww)
-        s = len(nodes)
-        if rows:
-            rows = np.asarray(rows, dtype=np.int64)
-            cols = np.asarray(cols, dtype=np.int64)
-            vals = np.asarray(vals, dtype=np.float64)
-            order = np.lexsort((gidx[cols], rows))          # by row, then by neighbour gene index
-            rows, cols, vals = rows[order], cols[order], vals[order]
-            counts = np.bincount(rows, minlength=s)
-        else:
-            cols = np.zeros(0, dtype=np.int64); vals = np.zeros(0); counts = np.zeros(s, dtype=np.int64)
-        base = row_ptr[-1]
-        row_ptr.extend((base + np.cumsum(counts)).tolist())
-        supp_all.append(gidx); col_all.append(cols); w_all.append(vals)
-        path_ptr.append(path_ptr[-1] + s)
-    cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dtype=dt)
-    return PackedPathways(len(Gs), n, path_ptr, cat(supp_all, np.int32), row_ptr,
-                          cat(col_all, np.int32), cat(w_all, np.float64))
+            ia, ib = lget(a), lget(b)
+            if ia is not None and ib is not None:
+                e_path.append(p); e_a.append(ia); e_b.append(ib); e_w.append(d.get("weight", 1))
+    path_ptr = np.zeros(P + 1, dtype=np.int64)
+    np.cumsum(sizes, out=path_ptr[1:])
+    support_idx = np.asarray(supp_all, dtype=np.int64)
+    S = int(path_ptr[-1])
+    if e_path:
+        ep = np.asarray(e_path, dtype=np.int64)
+        ea = np.asarray(e_a, dtype=np.int64); eb = np.asarray(e_b, dtype=np.int64)
+        ew = np.asarray(e_w, dtype=np.float64)
+        off = ea != eb                                           # an undirected edge counts both ways, a self loop once
+        rows = np.concatenate([ea, eb[off]]) + np.concatenate([path_ptr[ep], path_ptr[ep[off]]])   # packed row ids
+        cols = np.concatenate([eb, ea[off]])
+        vals = np.concatenate([ew, ew[off]])
+        base = np.concatenate([path_ptr[ep], path_ptr[ep[off]]])
+        order = np.lexsort((support_idx[base + cols], rows))     # by packed row, then by the neighbour's gene index
+        rows, cols, vals = rows[order], cols[order], vals[order]
+        counts = np.bincount(rows, minlength=S)
+    else:
+        cols = np.zeros(0, dtype=np.int64); vals = np.zeros(0); counts = np.zeros(S, dtype=np.int64)
+    row_ptr = np.zeros(S + 1, dtype=np.int64)
+    np.cumsum(counts, out=row_ptr[1:])
+    return PackedPathways(P, n, path_ptr, support_idx.astype(np.int32), row_ptr, cols.astype(np.int32), vals)

@@ -30,11 +30,13 @@ def add_prmf_arguments(parser):
     add("--tradeoff", default=-1, type=float,
         help="in [0,1]: re-derive gamma = delta from the last objective after every inner step (larger favours the "
              "manifold term); -1 (default) keeps them fixed")
-    add("--high-dimensional", default=True, type=_bool,
-        help="transpose the input if needed so that it has fewer rows than columns (default true)")
+    add("--high-dimensional", default=None, type=_bool,
+        help="true: transpose the input if it has more rows than columns; false: if it has fewer (the reference's rule, "
+             "prmf_runner.py:946-952).  Default: the matrix is taken as written, samples x genes -- the reference's default "
+             "of true would factor the transpose of a recount2-shape file and then fail writing U.csv (SURVEY 0.7)")
     add("--no-normalize", action='store_true', help="skip the quantile normalisation of the data")
     add("--normalize", action='store_true', help="no-op kept for the reference README's spelling; normalisation is on by default")
     add("--delimiter", default=",", help="field separator of --data")
-    add("--m-samples", type=int, help="read only this many leading rows of --data")
+    add("--m-samples", type=int, help="parsed and ignored, as in the reference (its value never reaches read_csv, prmf_runner.py:933-942)")
     add("--cross-validation", "-c", type=float, help="hold out this fraction of the samples and report their reconstruction error")
     add("--verbose", "-v", action='store_true', help="print the pathway assignments and objective parts of every iteration")

@@ -130,23 +130,18 @@ def nmf_init_v(X, u):
 
 
 DESCRIPTION = """
-B200-native implementation of Pathway-Regularized NMF (drop-in for gitter-lab/prmf prmf_runner.py).
+Pathway-regularised matrix factorisation on NVIDIA B200 GPUs: X (samples x genes) is approximated by U V^T with U >= 0,
+and every column of V is pulled towards the pathway graph it ends up assigned to.
 
-Solve an optimization problem of the form
-  min ||X - UV^T|| +
-    gamma * sum_k min_i V[:,k]^T Ls[i] V[:,k] +
-    delta * sum_k sum_{i | i in G_k} 1 / V[i,k] +
-    ||U||_F^2
+  objective = ||X - U V^T||_F  +  gamma * sum_k vhat_k^T Lhat_{p(k)} vhat_k  +  delta * sum_k sum_{i in p(k)} 1 / (vhat_ik + 1)
+              +  ||U||_F^2
 
-where Ls[i] is the Laplacian matrix associated with Gs[i],
-G_k is the manifold associated with latent factor k
-X has shape (n_obs, n_features),
-U has shape (n_obs, n_latent),
-V has shape (n_feature, n_latent)
+  p(k)   pathway assigned to factor k (sampled among the remaining candidates, pruned every 10 steps, matched at the end)
+  Lhat   normalised Laplacian of that pathway's graph, vhat_k = V[:,k] / ||V[:,k]||
+  U: samples x k     V: genes x k
 
-References
-----------
-Cai 2008. Non-negative Matrix Factorization on Manifold
+Same flags, inputs (--data, --manifolds *.graphml, --nodelist) and outputs (U.csv, V.csv, obj.txt) as prmf_runner.py of
+gitter-lab/prmf; the multiplicative updates follow Cai et al. 2008 (NMF on manifold).
 """
 
 
@@ -181,9 +176,9 @@ def main(argv=None):
     has_header = check_header(args.data, args.delimiter)                         # :928-929
     has_row_names = check_row_names(args.data, args.delimiter, has_header)
     X = pd.read_csv(args.data, sep=args.delimiter, header="infer" if has_header else None,
-                    nrows=args.m_samples, index_col=0 if has_row_names else None)  # :942
-    m, n = X.shape                                                               # :946-952
-    if (args.high_dimensional and m > n) or (not args.high_dimensional and m < n):
+                    nrows=None, index_col=0 if has_row_names else None)          # :942 (--m-samples never reaches it, :933-935)
+    m, n = X.shape                                                               # :946-952, only when the flag is given
+    if args.high_dimensional is not None and ((args.high_dimensional and m > n) or (not args.high_dimensional and m < n)):
         X = X.transpose()
     samples = list(X.index)
 
@@ -277,18 +272,22 @@ def main(argv=None):
     V_df = pd.DataFrame(V, index=nodelist, columns=cols)
     V_df.to_csv(V_fp, sep=",", index=True, quoting=csv.QUOTE_NONNUMERIC)
 
+    latent_to_pathway_data = obj_data.pop("latent_to_pathway_data", {})
+
+    def write_obj():                                                             # :1081-1093
+        with open(obj_fp, "w") as fh:
+            for key, val in obj_data.items():
+                fh.write("{} = {:0.5f}\n".format(key, val))
+            for k in sorted(latent_to_pathway_data.keys()):
+                lapl_ind = latent_to_pathway_data[k][0][0]
+                fh.write("{} -> {}\n".format(k, G_fp_pairs[lapl_ind][1]))
+
     if args.cross_validation is not None:                                        # :1074-1079
+        write_obj()              # a failure of the hold-out scoring must not lose the objective of a finished run
         errs = measure_cv_performance(V_df, X_test)
         np.savetxt(os.path.join(args.outdir, "test_error.csv"), errs, delimiter=",")
         obj_data["average_normalized_test_error"] = np.mean(errs)
-
-    with open(obj_fp, "w") as fh:                                                # :1081-1093
-        latent_to_pathway_data = obj_data.pop("latent_to_pathway_data", {})
-        for key, val in obj_data.items():
-            fh.write("{} = {:0.5f}\n".format(key, val))
-        for k in sorted(latent_to_pathway_data.keys()):
-            lapl_ind = latent_to_pathway_data[k][0][0]
-            fh.write("{} -> {}\n".format(k, G_fp_pairs[lapl_ind][1]))
+    write_obj()
 
 
 if __name__ == "__main__":

@@ -49,8 +49,9 @@ def test_flag_schema_matches_reference():
     assert flags == expected
     a = p.parse_args(["--data", "x", "--outdir", "o"])
     assert (a.k_latent, a.gamma, a.delta, a.tradeoff, a.high_dimensional, a.delimiter, a.tolerence) == (
-        6, 1.0, 1.0, -1, True, ",", 1e-3)
+        6, 1.0, 1.0, -1, None, ",", 1e-3)              # no transpose unless asked (the reference defaults to True)
     assert p.parse_args(["--data", "x", "--outdir", "o", "--high-dimensional", "False"]).high_dimensional is False
+    assert p.parse_args(["--data", "x", "--outdir", "o", "--high-dimensional", "True"]).high_dimensional is True
     assert p.parse_args(["--data", "x", "--outdir", "o", "--normalize"]).no_normalize is False
 
 
@@ -197,7 +198,7 @@ def test_random_restart_commands():
     b = q.parse_args(argv)                                          # the child accepts what the parent emits
     assert (b.data, b.k_latent, b.delimiter, b.no_normalize, b.seed, b.manifolds, b.manifolds_init) == (
         "d.tsv", 4, "\t", True, "7", ["a.graphml", "b.graphml"], [])
-    assert b.outdir == os.path.join("out", "run1") and b.high_dimensional is True
+    assert b.outdir == os.path.join("out", "run1") and b.high_dimensional is None
 
 
 @pytest.mark.gpu

@@ -66,6 +66,8 @@ for i in range(2, nh):                       # skip the first step (cold)
             row["producer dep satisfied after last exit of prev half"] = us(np.median(st[st[:, 7] > 0, 7]) - prev[pl, 6].max())
             row["entry after last exit of prev half (median)"] = us(np.median(s[:, 0]) - prev[pl, 6].max())
     lines.append(row)
+if not lines:
+    print("rank %d: no complete stamps" % ctx.rank); raise SystemExit(0)
 keys = [k for k in lines[0] if k not in ("half", "pass")]
 for ps in (1, 2):
     sel = [r for r in lines if r["pass"] == ps]

@@ -186,6 +186,7 @@ struct prmf_handle {
     unsigned int* err_host = nullptr;         // pinned host copy read at the end of every block
     unsigned long long spin_timeout_ns = 10000000000ull;
     bool failed = false;                      // a launch failed or a device wait expired: no further steps
+    double normX_sq_host = 0.0;               // ||X||^2 (all ranks), cached by prmf_set_X
     double* xbuf = nullptr;                   // push-exchange receive buffer inside p2p_buf
     size_t xcount = 0;
 
@@ -1078,6 +1079,25 @@ int check_err_word(prmf_handle* h, unsigned int errw) {
                 (errw & kErrTimeoutPeer) ? "waiting for a peer rank's exchange flag" : "");
 }
 
+// The hot loop takes recon^2 from the identity ||X||^2 - 2 sum(V*B) + tr(Gu Gv) (no pass over X).  When the fit is tight
+// (recon^2 below 1e-8 ||X||^2, e.g. noiseless low-rank data) the cancellation leaves few correct digits, and the value
+// drives the convergence test and the best-iterate choice of the driver (:745-774), which only look at the LAST step of
+// a block.  For that step U and V are still on the device: redo its recon with the explicit residual pass (:337).
+int refine_last_row(prmf_handle* h, int n_steps, double* obj_parts) {
+    if (!obj_parts || n_steps <= 0 || h->failed) return PRMF_OK;
+    double* row = obj_parts + (size_t)(n_steps - 1) * kObjStride;
+    const double r2 = row[7];
+    if (!(r2 < 1e-8 * h->normX_sq_host)) return PRMF_OK;
+    double exact = 0.0;
+    int rc = prmf_residual_sq(h, &exact);
+    if (rc) return rc;
+    const double recon = std::sqrt(exact > 0.0 ? exact : 0.0);
+    row[4] = recon + row[5] * row[1] + row[6] * row[2] + row[3];                   // :362
+    row[0] = recon;
+    row[7] = exact;
+    return PRMF_OK;
+}
+
 int collect(prmf_handle* h, int n_steps, double* obj_parts, double* gamma_delta_out) {
     CU(cudaSetDevice(h->device));
     if (n_steps > h->obj_capacity) return fail(h, PRMF_ERR_ARG, "collect: more steps than were run");
@@ -1089,7 +1109,9 @@ int collect(prmf_handle* h, int n_steps, double* obj_parts, double* gamma_delta_
     CU(cudaMemcpyAsync(&errw, h->err_word, sizeof errw, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     if (h->profiling) harvest_events(h);
-    return check_err_word(h, errw);
+    int rc_e = check_err_word(h, errw);
+    if (rc_e) return rc_e;
+    return refine_last_row(h, n_steps, obj_parts);
 }
 
 // ---- TF32 mode set-up ---------------------------------------------------------------------------------
@@ -1232,6 +1254,7 @@ int finish_X(prmf_handle* h) {
     }
     int rc = allreduce(h, h->normX_sq, 1);
     if (rc) return rc;
+    CU(cudaMemcpyAsync(&h->normX_sq_host, h->normX_sq, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->have_X = true;
     return PRMF_OK;
@@ -1835,7 +1858,9 @@ int prmf_block_end(prmf_handle* h, int n_steps, double* obj_parts, double* gamma
         CU(cudaStreamSynchronize(h->stream));
         harvest_events(h);
     }
-    return check_err_word(h, h->err_host ? *h->err_host : 0u);
+    int rc_e = check_err_word(h, h->err_host ? *h->err_host : 0u);
+    if (rc_e) return rc_e;
+    return refine_last_row(h, n_steps, obj_parts);
 }
 
 int prmf_snapshot_best(prmf_handle* h) {

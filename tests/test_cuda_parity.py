@@ -464,3 +464,26 @@ def test_score_tables_pathway_larger_than_staging_buffer():
         for p in range(len(Gs)):
             np.testing.assert_allclose(np.sqrt(mass[c, p]) + 1 - qn[c, p], O.score_match(tables, V[:, c], p), rtol=1e-12)
             np.testing.assert_allclose(qr[c, p], tables.Ls[p].dot(V[:, c]).dot(V[:, c]), rtol=1e-11)
+
+
+def test_tight_fit_recon_falls_back_to_the_explicit_residual():
+    """Noiseless low-rank X started next to its exact factors: recon^2 is ~1e-12 of ||X||^2, where the identity
+    ||X||^2 - 2 sum(V*B) + tr(Gu Gv) has no correct digits left.  The last step of a block (the one the driver's
+    convergence test and best-iterate choice read, :745-774) must then carry the explicit residual (:337)."""
+    from prmf_b200 import CudaEngine, pack_pathways, synth
+    rng = np.random.Generator(np.random.PCG64(8))
+    m, n, k = 400, 900, 5
+    Ut = rng.gamma(2.0, size=(m, k)); Vt = rng.gamma(2.0, size=(n, k))
+    X = Ut @ Vt.T
+    nodelist = list(range(n))
+    Gs = synth.random_pathway_graphs(rng, n, 6, median_size=12, sigma=0.2, lo=5, hi=20)
+    with CudaEngine(m, m, n, k) as eng:
+        eng.set_X(X); eng.set_pathways(pack_pathways(Gs, nodelist))
+        eng.set_UV(Ut * (1 + 1e-7 * rng.random((m, k))), Vt * (1 + 1e-7 * rng.random((n, k))))
+        eng.set_active([0, 1, 2, 3, 4])
+        parts, _, _ = eng.step(2, 1e-9, 1e-9)                    # negligible regularisation: the fit stays tight
+        U, V = eng.get_UV()
+    exact = np.linalg.norm(X - U @ V.T)
+    assert exact ** 2 < 1e-8 * np.linalg.norm(X) ** 2, "the instance is not in the cancellation regime"
+    np.testing.assert_allclose(parts[-1, 0], exact, rtol=1e-6)
+    np.testing.assert_allclose(parts[-1, 4], exact + parts[-1, 5] * parts[-1, 1] + parts[-1, 6] * parts[-1, 2] + parts[-1, 3], rtol=1e-12)

@@ -32,6 +32,22 @@ cudaError_t prmf_launch_block_kernel(int k, const BlockParams& prm, int grid, si
     }
 }
 
+namespace {
+__global__ void __launch_bounds__(64) small_allreduce_kernel(double* buf, int count, PeerSmall ps) {
+    const int t = threadIdx.x;
+    if (t >= count) return;
+    const size_t par = (size_t)(ps.seq & 1ull) * kMaxPeers;
+    const double v = buf[t];
+    for (int r = 0; r < ps.nranks; ++r) ll_store(ps.slot[r] + (par + ps.rank) * kSmallAllreduceMax + t, v, ps.seq);
+    buf[t] = ll_gather(ps.slot[ps.rank], par, kSmallAllreduceMax, ps.nranks, (size_t)t, ps.seq, ps.err, ps.timeout_ns);
+}
+}  // namespace
+
+cudaError_t prmf_launch_small_allreduce(double* buf, int count, const PeerSmall& ps, cudaStream_t stream) {
+    small_allreduce_kernel<<<1, 64, 0, stream>>>(buf, count, ps);
+    return cudaGetLastError();
+}
+
 #ifdef PRMF_BLOCK_TIMING
 extern "C" int prmf_debug_block_stamps(unsigned long long* out, int count, int reset) {
     if (reset) {

@@ -68,7 +68,19 @@ struct BlockParams {
     unsigned long long xbase;        // exchanges (= pass-2 executions of this kernel) before this launch
 };
 
+// sum over ranks of a few scalars through the peer buffers (no NCCL): [parity 2][source rank][kSmallAllreduceMax] entries
+constexpr int kSmallAllreduceMax = 64;
+struct PeerSmall {
+    ulonglong2* slot[kMaxPeers];
+    int nranks, rank;
+    unsigned long long seq;
+    unsigned int* err;
+    unsigned long long timeout_ns;
+};
+
 }  // namespace prmf
 
+// buf[0:count] <- sum over ranks, in rank order (count <= kSmallAllreduceMax); one small launch on `stream` (block.cu)
+cudaError_t prmf_launch_small_allreduce(double* buf, int count, const prmf::PeerSmall& ps, cudaStream_t stream);
 // Launches block_kernel<k> cooperatively (block.cu).  Returns cudaSuccess or the launch error.
 cudaError_t prmf_launch_block_kernel(int k, const prmf::BlockParams& prm, int grid, size_t smem, cudaStream_t stream);

@@ -103,7 +103,8 @@ __device__ bool cv_solve_passive(const double* __restrict__ sG, int k, const dou
             double s = sG[idx[i] * k + idx[j]];
             for (int t = 0; t < j; ++t) s -= L[i * k + t] * L[j * k + t];
             if (i == j) {
-                if (!(s > 0.0)) return false;
+                // not positive, or lost to cancellation: column i is (numerically) dependent on the ones before it
+                if (!(s > 1e-13 * sG[idx[i] * k + idx[i]])) return false;
                 L[i * k + i] = sqrt(s);
             } else {
                 L[i * k + j] = s / L[j * k + j];
@@ -151,19 +152,27 @@ __global__ void __launch_bounds__(64) cv_nnls_kernel(const double* __restrict__ 
         int enter = -1, np_ = 0;
         bool any = false;
         double best = 0.0;
+        // P[c]: 0 at its bound, 1 passive, 2 rejected in this round (its column depends on the passive ones)
         for (int c = 0; c < k; ++c) {
-            if (P[c]) { ++np_; continue; }
-            if (w[c] > tol) any = true;
+            if (P[c] == 1) { ++np_; continue; }
+            if (P[c] == 0 && w[c] > tol) any = true;
         }
         if (np_ == k || !any) break;
         for (int c = 0; c < k; ++c) {
-            const double wc = P[c] ? 0.0 : w[c];
-            if (enter < 0 || wc > best) { best = wc; enter = c; }
+            if (P[c] != 0) continue;
+            if (enter < 0 || w[c] > best) { best = w[c]; enter = c; }
         }
         P[enter] = 1;
         int p = 0;
-        for (int c = 0; c < k; ++c) { s[c] = 0.0; if (P[c]) idx[p++] = c; }
-        if (!cv_solve_passive(sG, k, b, idx, p, L, y)) { st = -2; break; }
+        for (int c = 0; c < k; ++c) { s[c] = 0.0; if (P[c] == 1) idx[p++] = c; }
+        if (!cv_solve_passive(sG, k, b, idx, p, L, y)) {
+            // Lawson & Hanson's independence test: a candidate whose column is (nearly) a combination of the passive
+            // columns cannot lower the residual -- leave it at zero and try the next largest dual
+            P[enter] = 2;
+            continue;
+        }
+        for (int c = 0; c < k; ++c)
+            if (P[c] == 2) P[c] = 0;
         for (int q = 0; q < p; ++q) s[idx[q]] = y[q];
         while (iter < maxiter) {
             double smin = DBL_MAX;
@@ -172,12 +181,12 @@ __global__ void __launch_bounds__(64) cv_nnls_kernel(const double* __restrict__ 
             ++iter;
             double alpha = DBL_MAX;
             for (int c = 0; c < k; ++c)
-                if (P[c] && s[c] < 0.0) alpha = fmin(alpha, x[c] / (x[c] - s[c]));
+                if (P[c] == 1 && s[c] < 0.0) alpha = fmin(alpha, x[c] / (x[c] - s[c]));
             for (int c = 0; c < k; ++c) { x[c] *= (1.0 - alpha); x[c] += alpha * s[c]; }
             for (int c = 0; c < k; ++c)
-                if (x[c] <= tol) P[c] = 0;
+                if (P[c] == 1 && x[c] <= tol) P[c] = 0;
             p = 0;
-            for (int c = 0; c < k; ++c) { if (P[c]) idx[p++] = c; }
+            for (int c = 0; c < k; ++c) { if (P[c] == 1) idx[p++] = c; }
             if (p > 0 && !cv_solve_passive(sG, k, b, idx, p, L, y)) { st = -2; break; }
             for (int c = 0; c < k; ++c) s[c] = 0.0;
             for (int q = 0; q < p; ++q) s[idx[q]] = y[q];

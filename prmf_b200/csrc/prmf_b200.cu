@@ -188,6 +188,8 @@ struct prmf_handle {
     bool failed = false;                      // a launch failed or a device wait expired: no further steps
     double normX_sq_host = 0.0;               // ||X||^2 (all ranks), cached by prmf_set_X
     double* xbuf = nullptr;                   // push-exchange receive buffer inside p2p_buf
+    double* xsmall = nullptr;                 // receive slots of the small all-reduce (set-up scalars without NCCL)
+    unsigned long long small_seq = 0;
     size_t xcount = 0;
 
     // single-pass fused X kernel (opt-in: PRMF_FUSED=1)
@@ -838,11 +840,16 @@ int launch_scores(prmf_handle* h) {
 }
 
 // persistent step kernel: halves [h0, h0 + nh) of a block in one cooperative launch (block.cuh / block.cu)
+// Rows of X are sharded over ranks: with an NCCL communicator, or with the NVLink / IPC peer buffers alone (then every
+// reduction over ranks -- the per-step one inside the persistent step kernel and the few set-up scalars -- goes through
+// peer memory and NCCL is not needed at all, e.g. ranks that share one device in a test).
+bool sharded(const prmf_handle* h) { return h->nranks > 1 && (h->comm != nullptr || h->p2p_ready); }
+
 // The persistent step kernel is the default for sharded runs (there the exchange lives inside it); on one GPU it
 // times like the two-launch path and draws more power in sustained runs, so it is opt-in there (PRMF_BLOCK=1).
 bool block_path(const prmf_handle* h) {
     if (!h->use_block) return false;
-    if (h->comm == nullptr) return h->block_forced;
+    if (!sharded(h)) return h->block_forced;
     return h->blk_xchg;
 }
 
@@ -872,7 +879,7 @@ int launch_block(prmf_handle* h, int h0, int nh) {
     prm.hist_Gu = h->hist_Gu; prm.hist_Gvp = h->hist_Gvp; prm.hist_VBp = h->hist_VBp; prm.hist_vh = h->hist_vh;
     prm.doff = h->as_off;
     prm.err = h->err_word; prm.timeout_ns = h->spin_timeout_ns;
-    prm.nranks = h->comm ? h->nranks : 1; prm.rank = h->rank;
+    prm.nranks = sharded(h) ? h->nranks : 1; prm.rank = h->rank;
     if (prm.nranks > 1) {
         const size_t off_buf = (size_t)(h->xbuf - h->p2p_buf);                 // same layout in every rank's buffer
         for (int r = 0; r < h->nranks; ++r) prm.xbuf[r] = (ulonglong2*)((double*)h->peer_base[r] + off_buf);
@@ -922,7 +929,21 @@ int prefetch_pass1(prmf_handle* h) {
 }
 
 int allreduce(prmf_handle* h, double* buf, size_t count) {
-    if (!h->comm) return PRMF_OK;
+    if (!h->comm) {
+        if (!sharded(h)) return PRMF_OK;
+        // no NCCL: the few set-up scalars (||X||^2, the agreement of prmf_p2p_finalize, a verification residual) are summed
+        // over the peer buffers with the same {value, sequence} entries as the per-step exchange
+        if (count > (size_t)kSmallAllreduceMax) return fail(h, PRMF_ERR_STATE, "reduction of %zu values over ranks needs NCCL", count);
+        PeerSmall ps{};
+        const size_t off = (size_t)(h->xsmall - h->p2p_buf);
+        for (int r = 0; r < h->nranks; ++r) ps.slot[r] = (ulonglong2*)((double*)h->peer_base[r] + off);
+        ps.nranks = h->nranks; ps.rank = h->rank; ps.seq = ++h->small_seq;
+        ps.err = h->err_word; ps.timeout_ns = h->spin_timeout_ns;
+        cudaError_t e_ = prmf_launch_small_allreduce(buf, (int)count, ps, h->stream);
+        if (e_ != cudaSuccess) return fail(h, PRMF_ERR_CUDA, "peer all-reduce launch failed: %s", cudaGetErrorString(e_));
+        h->launches++;
+        return PRMF_OK;
+    }
     int r = g_nccl.AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, h->comm, h->stream);
     if (r != 0)
         return fail(h, PRMF_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
@@ -984,7 +1005,7 @@ int enqueue_steps(prmf_handle* h, int n_steps, double gamma, double delta, doubl
         cudaEventRecord(h->ev_pool[h->ev_pairs.back().second + 1], h->stream);
     };
     // deferred objective: one GPU, or sharded with the in-kernel exchange (every rank evaluates the same numbers)
-    const bool defer = h->defer_ok && h->use_epi && (h->comm == nullptr || h->use_xchg || h->blk_xchg) && tradeoff < 0.0 &&
+    const bool defer = h->defer_ok && h->use_epi && (!sharded(h) || h->use_xchg || h->blk_xchg) && tradeoff < 0.0 &&
                        !h->profiling && h->as.n_diag <= kVhCap;
     if (defer && block_path(h)) {
         // the whole block in ONE persistent launch (block.cuh) + the deferred objective
@@ -997,6 +1018,9 @@ int enqueue_steps(prmf_handle* h, int n_steps, double gamma, double delta, doubl
         LAUNCH_CHECK("objective_deferred_kernel");
         return PRMF_OK;
     }
+    if (sharded(h) && !h->comm)
+        return fail(h, PRMF_ERR_STATE, "without an NCCL communicator a sharded handle can only run the persistent step kernel "
+                                       "(k <= 10, fixed gamma / delta, no per-phase profiling); call prmf_comm_init for this configuration");
     for (int s = 0; s < n_steps; ++s) {
         const bool skip_pass1 = s == 0 && h->ahead != 0;      // already enqueued by prmf_block_end
         if (skip_pass1) h->ahead = 0;
@@ -1007,7 +1031,7 @@ int enqueue_steps(prmf_handle* h, int n_steps, double gamma, double delta, doubl
                 rc = s == 0 ? launch_xv_epi(h) : launch_xv_epi(h, h->hist_Gvp + (size_t)(s - 1) * h->tpanels * kk2s, h->tpanels);
                 if (rc) return rc;
             }
-            if ((rc = launch_xtu_epi(h, h->comm == nullptr ? 2 : 4, nullptr, s))) return rc;
+            if ((rc = launch_xtu_epi(h, !sharded(h) ? 2 : 4, nullptr, s))) return rc;
             if (s == n_steps - 1) {
                 objective_deferred_kernel<<<n_steps, kTailThreads, obj_smem(h), h->stream>>>(
                     h->k, h->hist_Gu, h->hist_Gvp, h->hist_VBp, h->tpanels, h->hist_vh, kVhCap, h->normX_sq, h->as, h->Gv,
@@ -1019,7 +1043,7 @@ int enqueue_steps(prmf_handle* h, int n_steps, double gamma, double delta, doubl
         if (h->use_epi) {
             if (!skip_pass1) { tic(0); rc = launch_xv_epi(h); toc(); }
             if (rc) return rc;
-            if (h->comm == nullptr) {
+            if (!sharded(h)) {
                 tic(2); rc = launch_xtu_epi(h, 2, nullptr); toc();               // + V update
                 if (rc) return rc;
                 tic(5); rc = launch_objective(h, tradeoff, h->Gu_part, h->tpanels1); toc();
@@ -1053,8 +1077,8 @@ int enqueue_steps(prmf_handle* h, int n_steps, double gamma, double delta, doubl
             tic(2); rc = launch_xtu(h); toc();
             if (rc) return rc;
         }
-        const bool sharded = h->comm != nullptr;
-        if (sharded) {
+        const bool is_sharded = sharded(h);
+        if (is_sharded) {
             tic(3);
             double* dst = h->p2p_ready ? h->p2p_buf + (size_t)h->p2p_parity * h->p2p_red_count : h->red;
             reduce_pack_kernel<<<(unsigned)((nk + kk2 + 2 + 255) / 256), 256, 0, h->stream>>>(
@@ -1065,7 +1089,7 @@ int enqueue_steps(prmf_handle* h, int n_steps, double gamma, double delta, doubl
             toc();
             if (rc) return rc;
         }
-        tic(4); rc = launch_v_update_objective(h, sharded, tradeoff); toc();
+        tic(4); rc = launch_v_update_objective(h, is_sharded, tradeoff); toc();
         if (rc) return rc;
     }
     return PRMF_OK;
@@ -1998,11 +2022,13 @@ int prmf_p2p_export(prmf_handle* h, uint8_t* handle_out) {
         // push exchange of the persistent step kernel: receive slots [parity][source rank][n*k + k*k] + its flags
         h->xcount = h->p2p_red_count;
         const size_t xdoubles = 2 * 2 * (size_t)kMaxPeers * h->xcount;        // 16-byte {value, sequence} entries
-        const size_t total = ((old_total + 1) & ~(size_t)1) + xdoubles;
+        const size_t sdoubles = 2 * 2 * (size_t)kMaxPeers * kSmallAllreduceMax;   // set-up scalars without NCCL
+        const size_t total = ((old_total + 1) & ~(size_t)1) + xdoubles + sdoubles;
         int rc = dalloc(h, &h->p2p_buf, total);
         if (rc) return rc;
         CU(cudaMemset(h->p2p_buf, 0, total * sizeof(double)));
         h->xbuf = h->p2p_buf + ((old_total + 1) & ~(size_t)1);                // 16-byte aligned
+        h->xsmall = h->xbuf + xdoubles;
     }
     cudaIpcMemHandle_t hd;
     CU(cudaIpcGetMemHandle(&hd, h->p2p_buf));
@@ -2036,7 +2062,7 @@ int prmf_p2p_attach(prmf_handle* h, int rank, int nranks, const uint8_t* handles
 
 int prmf_p2p_finalize(prmf_handle* h) {
     if (!h) return PRMF_ERR_ARG;
-    if (!h->p2p_ready || !h->comm) return fail(h, PRMF_ERR_STATE, "prmf_p2p_finalize needs prmf_comm_init and prmf_p2p_attach");
+    if (!h->p2p_ready) return fail(h, PRMF_ERR_STATE, "prmf_p2p_finalize needs prmf_p2p_attach (and prmf_comm_init unless NCCL is not used)");
     CU(cudaSetDevice(h->device));
     // the in-kernel exchange is used only if EVERY rank runs the fused-tail path (ranks that disagreed would wait
     // on flags nobody writes)
@@ -2059,7 +2085,7 @@ int prmf_p2p_finalize(prmf_handle* h) {
 }
 
 int prmf_exchange_mode(const prmf_handle* h) {
-    if (!h || !h->comm) return 0;
+    if (!h || !sharded(h)) return 0;
     if (!h->p2p_ready) return 1;
     if (h->blk_xchg && h->use_block) return 4;
     return h->use_xchg ? 3 : 2;

@@ -40,8 +40,8 @@ def nnls_rows(V, X, device=None):
         raise _lib.PrmfLibraryError("prmf_nnls_rows failed (%d): %s" % (rc, lib.prmf_cv_last_error().decode()))
     if (status == -1).any():
         raise RuntimeError("Maximum number of iterations reached.")          # scipy's message
-    if (status == -2).any():
-        raise np.linalg.LinAlgError("V^T V is singular on a passive set (V has dependent columns)")
+    if (status == -2).any():          # (dependent columns are handled inside the solver; this is a numerical breakdown)
+        raise np.linalg.LinAlgError("V^T V lost positive definiteness on a passive set")
     return U, rnorm, np.sqrt(xx)
 
 

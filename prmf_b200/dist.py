@@ -36,12 +36,16 @@ class DistContext:
         import torch.distributed as dist
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl" and torch.cuda.device_count() < world:
+            backend = "gloo"             # NCCL cannot put two ranks on one device; the process group is plumbing only
         if init and not dist.is_initialized():
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             kw = {}
             if backend == "nccl":
                 torch.cuda.set_device(local_rank)
                 kw["device_id"] = torch.device("cuda", local_rank)
+            elif torch.cuda.is_available():
+                torch.cuda.set_device(local_rank % torch.cuda.device_count())
             dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
         return cls(rank, world, local_rank, backend)
 

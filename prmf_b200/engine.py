@@ -41,6 +41,7 @@ class CudaEngine:
             msg = self.lib.prmf_last_error(None)
             raise _lib.PrmfLibraryError("prmf_create failed (%d): %s" % (rc, msg.decode() if msg else "?"))
         self.h = h
+        self.device = int(device)
         self._keep = None
 
     # -- lifetime ------------------------------------------------------------------------------------
@@ -240,6 +241,16 @@ class CudaEngine:
         return self.lib.prmf_stream(self.h)
 
 
+def _device_identity(eng):
+    """Something that is equal exactly for ranks whose engines sit on the same physical GPU."""
+    try:
+        import torch
+        return str(torch.cuda.get_device_properties(eng.device).uuid)
+    except Exception:
+        import os
+        return "%s:%d" % (os.environ.get("CUDA_VISIBLE_DEVICES", ""), eng.device)
+
+
 def nccl_unique_id():
     """128-byte NCCL unique id (rank 0 creates it and ships it to the other ranks)."""
     lib = _lib.load()
@@ -276,11 +287,19 @@ def attach_collectives(eng, ctx, p2p=None):
     import os
     if ctx.world <= 1:
         return eng
-    nccl_load()
-    uid = ctx.broadcast_bytes(nccl_unique_id() if ctx.rank == 0 else None, src=0)
-    eng.attach_comm(ctx.rank, ctx.world, uid)
+    # NCCL refuses two ranks on one device; ranks that share a GPU (a one-GPU test box) -- or PRMF_NCCL=0 -- run on the
+    # peer buffers alone: the per-step exchange lives in the persistent step kernel anyway, and the few set-up scalars
+    # are summed through the same buffers (the library reports what it cannot do without a communicator)
+    devices = ctx.all_gather_bytes(_device_identity(eng).encode())
+    use_nccl = os.environ.get("PRMF_NCCL", "1") != "0" and len(set(devices)) == len(devices)
+    if use_nccl:
+        nccl_load()
+        uid = ctx.broadcast_bytes(nccl_unique_id() if ctx.rank == 0 else None, src=0)
+        eng.attach_comm(ctx.rank, ctx.world, uid)
     if p2p is None:
         p2p = os.environ.get("PRMF_P2P", "1") != "0"
+    if not use_nccl and not (p2p and ctx.world <= 8):
+        raise _lib.PrmfLibraryError("ranks share a device (or PRMF_NCCL=0): the run needs the peer-memory exchange (PRMF_P2P)")
     if p2p and ctx.world <= 8:
         handles = ctx.all_gather_bytes(eng.p2p_export())
         ok = True

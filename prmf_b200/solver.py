@@ -33,9 +33,21 @@ def _obj_dict(row):
 
 def default_engine_factory(m_local, m_global, n, k, ctx, x_dtype="f64"):
     """One CUDA engine per rank; with more than one rank the engines share an NCCL communicator."""
-    device = ctx.local_rank if ctx.world > 1 else _current_device()
+    device = _rank_device(ctx) if ctx.world > 1 else _current_device()
     eng = CudaEngine(m_local, m_global, n, k, device=device, x_dtype=x_dtype)
     return attach_collectives(eng, ctx)
+
+
+def _rank_device(ctx):
+    """One GPU per rank; ranks beyond the visible devices wrap around (several ranks on one GPU: tests on a one-GPU box)."""
+    try:
+        import torch
+        n = torch.cuda.device_count()
+        if n > 0:
+            return ctx.local_rank % n
+    except ImportError:
+        pass
+    return ctx.local_rank
 
 
 def _current_device():

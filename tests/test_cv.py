@@ -54,3 +54,21 @@ def test_batched_nnls_edge_cases():
         nnls_rows(V, rng.random((3, 49)))
     with pytest.raises(ValueError):
         nnls_rows(V, np.full((2, 50), np.nan))
+
+
+@pytest.mark.gpu
+def test_batched_nnls_dependent_columns():
+    """V with duplicated / linearly dependent columns (V^T V singular): scipy's nnls copes; the batched solver must too
+    (the minimiser is not unique there, the residual is)."""
+    import scipy.optimize
+    from prmf_b200 import nnls_rows
+    rng = np.random.Generator(np.random.PCG64(21))
+    base = rng.random((200, 5))
+    V = np.hstack([base, base[:, :2], (base[:, 2] + base[:, 3])[:, None]])     # columns 5, 6 duplicate 0, 1; 7 = 2 + 3
+    X = rng.random((30, 5)) @ base.T + 0.02 * rng.standard_normal((30, 200))
+    U, rnorm, xnorm = nnls_rows(V, X)
+    assert (U >= 0).all()
+    for i in range(X.shape[0]):
+        _, e = scipy.optimize.nnls(V, X[i])
+        np.testing.assert_allclose(rnorm[i], e, rtol=1e-7)
+        np.testing.assert_allclose(np.linalg.norm(X[i] - V @ U[i]), e, rtol=1e-7)

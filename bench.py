@@ -579,8 +579,24 @@ def run_ours(a):
         Uh.copy_(torch.from_numpy(np.ascontiguousarray(U0[lo:hi]))); Vh.copy_(torch.from_numpy(V0))
         Xn, Un, Vn = Xh.numpy(), Uh.numpy(), Vh.numpy()
 
-        def e2e_iteration():
-            eng.set_X(Xn)                       # H2D of this step's input
+        # Every step uploads its X from pinned host memory (H2D inside the timed region) -- into one of two device staging
+        # buffers on a copy stream, so that the upload of step i+1 overlaps the compute of step i (the first upload is
+        # exposed and counted); the engine then takes the staged block (device-to-device + transposed copy), runs the
+        # step and the result is read back.
+        copy_stream = torch.cuda.Stream(device=dev)
+        stage = [torch.empty((m_local, a.n), dtype=xdt, device="cuda") for _ in range(2)]
+        staged = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def start_upload(i):
+            with torch.cuda.stream(copy_stream):
+                stage[i % 2].copy_(Xh, non_blocking=True)
+                staged[i % 2].record(copy_stream)
+
+        def e2e_iteration(i, last):
+            staged[i % 2].synchronize()         # this step's X has arrived
+            if not last:
+                start_upload(i + 1)             # the next step's upload runs under this step's compute
+            eng.set_X(stage[i % 2])
             eng.set_UV(Un, Vn)
             active = sample_active(full_cands, a.k)
             eng.set_active(active)
@@ -590,21 +606,25 @@ def run_ours(a):
             Uo, Vo = eng.get_UV()               # D2H of the result
             return float(p[-1, 4]), Uo, Vo
 
-        n_e2e = max(2, min(a.steps, 5))
-        e2e_iteration()
+        n_e2e = max(2, a.steps)
+        start_upload(0); e2e_iteration(0, True)                      # warm-up
         sync_all()
         t0 = time.perf_counter()
         e0.record(stream)
-        for _ in range(n_e2e):
-            e2e_iteration()
+        start_upload(0)
+        for i in range(n_e2e):
+            e2e_iteration(i, i == n_e2e - 1)
         e1.record(stream)
         sync_all()
         wall_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
-        ems = max_over_ranks(max(e0.elapsed_time(e1) / n_e2e, wall_ms))
+        ems = max_over_ranks(wall_ms)           # wall clock: the copy stream's work is part of the step
+        del stage
         e2e = {"value": 1000.0 / ems, "unit": UNIT, "ms_per_step": ems,
                "h2d_bytes_per_step": int(m_local * a.n * xsz + (m_local + a.n) * a.k * 8),
                "d2h_bytes_per_step": int((m_local + a.n) * a.k * 8 + MODULUS * 64 + 2 * a.k * packed.P * 8),
-               "steps": n_e2e}
+               "steps": n_e2e,
+               "note": "X of every step uploaded from pinned host memory (double-buffered: the upload of step i+1 overlaps "
+                       "the compute of step i, the first one is exposed), U / V in and out, objective out; PCIe-bound"}
 
     # ---- time to converge: the public entry point on the planted instance, host arrays in and out ----
     ttc = None

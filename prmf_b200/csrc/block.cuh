@@ -25,40 +25,6 @@
 
 namespace prmf {
 
-__device__ __forceinline__ unsigned long long blk_gtime() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-
-__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-
-// Spin until *p >= target (acquire; SYS: the writer is a peer GPU).  Gives up when the deadline passes or when
-// another waiter of this kernel already gave up (err != 0), so a failed launch drains instead of hanging.
-template <bool SYS>
-__device__ __forceinline__ bool blk_wait_ge(const unsigned long long* p, unsigned long long target, unsigned int* err,
-                                            unsigned long long timeout_ns) {
-    unsigned long long t0 = 0;
-    unsigned int polls = 0;
-    for (;;) {
-        const unsigned long long v = SYS ? ld_acquire_sys_u64(p) : ld_acquire_gpu_u64(p);
-        if (v >= target) return true;
-        __nanosleep(40);                          // a spinning warp costs issue slots and power on its SM
-        if ((++polls & 255u) == 0u) {
-            const unsigned long long now = blk_gtime();
-            if (t0 == 0) t0 = now;
-            if (now - t0 > timeout_ns || ld_volatile_u32(err) != 0u) {
-                atomicOr(err, SYS ? kErrTimeoutPeer : kErrTimeoutLocal);
-                return false;
-            }
-        }
-    }
-}
-
 // Low-latency exchange entries: a value travels with its sequence number in ONE 16-byte store, so the receiver needs
 // neither a fence nor a separate flag -- it polls the entry itself until the sequence number is the expected one
 // (one one-way NVLink hop; the pattern of NCCL's LL protocol, here with 8-byte payloads).

@@ -12,8 +12,6 @@ constexpr int kBlkTile = 85;         // small shares (many chunks): rows per til
 constexpr int kBlkPre = 51;          // largest pass-2 share the helper warp prefetches (five staged arrays share that scratch)
 constexpr int kBlkThreads = 320;     // 8 consumer warps + the TMA producer warp + the helper warp
 
-constexpr unsigned int kErrTimeoutLocal = 1u;   // a wait on another CTA of this GPU expired
-constexpr unsigned int kErrTimeoutPeer = 2u;    // a wait on a peer GPU's flag expired
 
 struct BlockParams {
     // X (m x n, leading dimension ldx) and its transposed copy (n x m, ldxt)

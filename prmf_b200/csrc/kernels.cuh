@@ -417,6 +417,62 @@ constexpr int kTmaThreads = (kTmaConsumerWarps + 1) * 32;
 // ----------------------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 8;
 
+// ---- bounded device-side waits ------------------------------------------------------------------------
+// Every spin wait on a counter or flag written by another thread block or another GPU has a %globaltimer deadline:
+// on expiry the waiter sets an error word, stops waiting (so do all later waits of the launch) and the kernel drains;
+// the host turns the word into PRMF_ERR_TIMEOUT.  A lost launch or a dead peer rank is an error code, not a hang.
+constexpr unsigned int kErrTimeoutLocal = 1u;   // a wait on another CTA of this GPU expired
+constexpr unsigned int kErrTimeoutPeer = 2u;    // a wait on a peer GPU's flag expired
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long blk_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// Spin until *p >= target (acquire; SYS: the writer is a peer GPU).  Gives up when the deadline passes or when
+// another waiter of this kernel already gave up (err != 0), so a failed launch drains instead of hanging.
+template <bool SYS>
+__device__ __forceinline__ bool blk_wait_ge(const unsigned long long* p, unsigned long long target, unsigned int* err,
+                                            unsigned long long timeout_ns) {
+    unsigned long long t0 = 0;
+    unsigned int polls = 0;
+    for (;;) {
+        const unsigned long long v = SYS ? ld_acquire_sys_u64(p) : ld_acquire_gpu_u64(p);
+        if (v >= target) return true;
+        __nanosleep(40);                          // a spinning warp costs issue slots and power on its SM
+        if ((++polls & 255u) == 0u) {
+            const unsigned long long now = blk_gtime();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > timeout_ns || ld_volatile_u32(err) != 0u) {
+                atomicOr(err, SYS ? kErrTimeoutPeer : kErrTimeoutLocal);
+                return false;
+            }
+        }
+    }
+}
+
+
+
 
 
 struct PeerExchange {
@@ -425,6 +481,8 @@ struct PeerExchange {
     const double* red[kMaxPeers];              // rank r's packed buffer of this step's parity (P2P mapped)
     unsigned long long* flags[kMaxPeers];      // rank r's flag array: flags[r][q] = last step rank q announced
     unsigned long long seq;                    // this step's sequence number (monotone)
+    unsigned int* err;                         // bounded waits: error word and deadline
+    unsigned long long timeout_ns;
 };
 
 __device__ __forceinline__ double ld_peer(const double* p) {
@@ -440,11 +498,7 @@ __device__ __forceinline__ void peer_barrier(const PeerExchange& px) {
             __threadfence_system();
             asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(px.flags[threadIdx.x] + px.rank), "l"(px.seq) : "memory");
         }
-        const unsigned long long* mine = px.flags[px.rank] + threadIdx.x;
-        unsigned long long seen;
-        do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
-        } while (seen < px.seq);
+        blk_wait_ge<true>(px.flags[px.rank] + threadIdx.x, px.seq, px.err, px.timeout_ns);
     }
     __syncthreads();
 }
@@ -514,6 +568,8 @@ struct EpiParams {
                                   // rank q published the segment of CTA c (c == ctas: its Gu)
     double* Gu_glob;              // out: U^T U summed over ranks (k*k), for the objective kernel
     int dbg_slot;                 // developer timing builds only: timeline slot of this launch (-1: none)
+    unsigned int* err;            // bounded waits: error word and deadline
+    unsigned long long timeout_ns;
 };
 
 __device__ __forceinline__ void cons_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -537,11 +593,6 @@ __device__ unsigned long long g_kt_dbg[64 * 4];
 #define KT_STAMP_MAX(slot, i) do { } while (0)
 #endif
 
-__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 
 // fixed-order sum of `count` partials read from L2 (they were just written by other SMs)
 __device__ __forceinline__ double sum_strided_cg(const double* __restrict__ part, int count, int64_t stride) {
@@ -564,8 +615,7 @@ __device__ __forceinline__ void epi_panel_barrier(const EpiParams& ep, int panel
     cons_bar();
     if (threadIdx.x == 0) {
         atomicAdd(ep.arrive + panel, 1ull);
-        const unsigned long long target = ep.seq * gridDim.y;
-        while (ld_acquire_gpu_u64(ep.arrive + panel) < target) { }
+        blk_wait_ge<false>(ep.arrive + panel, ep.seq * gridDim.y, ep.err, ep.timeout_ns);
     }
     cons_bar();
 }
@@ -775,14 +825,6 @@ __device__ __forceinline__ void epi_pack(const EpiParams& ep, int panel, int64_t
     }
 }
 
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 
 template <int K>
 __device__ __forceinline__ void epi_exchange_v_update(const EpiParams& ep, unsigned char* smem, int* s_flag, int panel,
@@ -824,11 +866,9 @@ __device__ __forceinline__ void epi_exchange_v_update(const EpiParams& ep, unsig
     if (cta == 0 && t >= 32 && t < 32 + px.nranks)
         st_release_sys_u64(ep.xflags[t - 32] + (size_t)px.rank * fstride + ncta, px.seq);
     if (t < px.nranks) {
-        const unsigned long long* f = ep.xflags[px.rank] + (size_t)t * fstride + cta;
-        while (ld_acquire_sys_u64(f) < px.seq) { }
+        blk_wait_ge<true>(ep.xflags[px.rank] + (size_t)t * fstride + cta, px.seq, ep.err, ep.timeout_ns);
     } else if (t >= 32 && t < 32 + px.nranks) {
-        const unsigned long long* f = ep.xflags[px.rank] + (size_t)(t - 32) * fstride + ncta;
-        while (ld_acquire_sys_u64(f) < px.seq) { }
+        blk_wait_ge<true>(ep.xflags[px.rank] + (size_t)(t - 32) * fstride + ncta, px.seq, ep.err, ep.timeout_ns);
     }
     cons_bar();
     EPI_STAMP(3);

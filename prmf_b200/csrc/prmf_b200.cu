@@ -331,6 +331,7 @@ int launch_skinny_tma_t(prmf_handle* h, const double* M, int64_t ldm, int64_t ro
     dim3 grid(panels, chunks);
     EpiParams none{};
     none.dbg_slot = -1;
+    none.err = h->err_word; none.timeout_ns = h->spin_timeout_ns;
     if (h->tma_rs == 4) {
         CU(cudaFuncSetAttribute(skinny_tma_kernel<KT, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         skinny_tma_kernel<KT, 4, 0><<<grid, kTmaThreads, smem, h->stream>>>(M, ldm, rows, cols, W, panel_w, rows_per_chunk,
@@ -594,6 +595,7 @@ int launch_v_update_objective(prmf_handle* h, bool sharded, double tradeoff) {
         px.nranks = h->nranks;
         px.rank = h->rank;
         px.seq = ++h->p2p_seq;
+        px.err = h->err_word; px.timeout_ns = h->spin_timeout_ns;
         for (int r = 0; r < h->nranks; ++r) {
             double* base = (double*)h->peer_base[r];
             px.red[r] = base + (size_t)h->p2p_parity * h->p2p_red_count;
@@ -720,6 +722,7 @@ int ensure_pos(prmf_handle* h) {
 // ---- fused-tail path (use_epi): two X-stream launches per inner step do the U and V updates as well ----
 int launch_xv_epi(prmf_handle* h, const double* gv_src = nullptr, int gv_parts = 1) {
     EpiParams ep{};
+    ep.err = h->err_word; ep.timeout_ns = h->spin_timeout_ns;
     const size_t np = (size_t)h->tpanels1 + h->tpanels;
     ep.arrive = h->epi_counters;
     ep.done = h->epi_counters + np;
@@ -744,6 +747,7 @@ int launch_xv_epi(prmf_handle* h, const double* gv_src = nullptr, int gv_parts =
 // mode 2: V update (one GPU); 3: pack into `packed_dst` (NCCL path); 4: NVLink peer exchange + V update
 int launch_xtu_epi(prmf_handle* h, int mode, double* packed_dst, int hist_slot = -1) {
     EpiParams ep{};
+    ep.err = h->err_word; ep.timeout_ns = h->spin_timeout_ns;
     const size_t np = (size_t)h->tpanels1 + h->tpanels;
     ep.arrive = h->epi_counters + h->tpanels1;
     ep.done = h->epi_counters + np + h->tpanels1;

@@ -64,16 +64,17 @@ def test_hot_kernels_use_the_claimed_hardware_paths():
         assert any(op.startswith(needle) for op in tc), needle
 
 
-def test_persistent_kernel_main_loop_is_clean():
+def test_stream_kernel_main_loops_are_clean():
     funcs = _sass_by_function()
     for k in (6, 10):
-        name = [n for n in funcs if "block_kernelILi%dE" % k in n][0]
+      for pattern in ("block_kernelILi%dE" % k, "skinny_tma_kernelILi%dELi8ELi1E" % k, "skinny_tma_kernelILi%dELi8ELi2E" % k):
+        name = [n for n in funcs if pattern in n][0]
         ops = funcs[name]
         a, b = _longest_dfma_region(ops)
         loop = ops[a:b + 1]
         n_dfma = sum(op.startswith("DFMA") for op in loop)
-        assert n_dfma >= 8 * 4 * k                                          # the 8-row stage, 4 columns per thread
-        assert not any(op.startswith(("LDL", "STL")) for op in loop), "spills inside the X-stream main loop (k=%d)" % k
+        assert n_dfma >= 8 * 4 * k, pattern                                 # the 8-row stage, 4 columns per thread
+        assert not any(op.startswith(("LDL", "STL")) for op in loop), "spills inside the X-stream main loop of %s" % pattern
         moves = sum(op.startswith(("IMAD.MOV", "MOV")) for op in loop)
-        assert moves <= n_dfma // 8, "register-move storm inside the main loop: %d moves for %d DFMA" % (moves, n_dfma)
-        assert sum(op.startswith("LDS.128") for op in loop) >= 8 * (2 + (k // 2 if k % 2 == 0 else 0)) - 16
+        assert moves <= n_dfma // 8, "register-move storm inside the main loop of %s: %d moves for %d DFMA" % (pattern, moves, n_dfma)
+        assert sum(op.startswith("LDS.128") for op in loop) >= 8 * (2 + (k // 2 if k % 2 == 0 else 0)) - 16, pattern

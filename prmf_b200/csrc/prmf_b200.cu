@@ -38,16 +38,16 @@ struct DevBuf {
     size_t bytes = 0;
 };
 
-// Cache of the large per-handle device buffers (X and its transposed copy) across handles of one process:
-// cudaMalloc / cudaFree of multi-GB buffers cost from a few ms to a second each on these boxes, which is most of the
-// wall time of a short solve that creates and destroys a handle (random restarts, repeated solves of one instance).
-// A freed buffer is kept (bounded count and bytes) and handed to the next handle that asks for the same size on the
-// same device.  PRMF_POOL=0 disables it; prmf_release_pool() returns everything to the driver.
+// Cache of a handle's device allocations (X, its transposed copy, the arenas of the small state) across handles of one
+// process: every cudaMalloc / cudaFree costs 10-100 ms on these boxes (multi-GB ones up to a second), which is most of
+// the wall time of a short solve that creates and destroys a handle (random restarts, repeated solves of one
+// instance).  A freed buffer is kept (bounded count and bytes) and handed to the next request of the same size on
+// the same device.  PRMF_POOL=0 disables it; prmf_release_pool() returns everything to the driver.
 struct BigPool {
     struct Ent { void* p; size_t bytes; int device; };
     std::vector<Ent> free_list;
     size_t held = 0;
-    static constexpr size_t kMaxEntries = 4;
+    static constexpr size_t kMaxEntries = 16;
     static constexpr size_t kMaxBytes = (size_t)24 << 30;
     bool enabled() const { const char* e = getenv("PRMF_POOL"); return !(e && atoi(e) == 0); }
     cudaError_t alloc(void** out, size_t bytes, int device) {
@@ -78,6 +78,17 @@ struct BigPool {
 };
 BigPool g_pool;
 
+// pinned host words (one per handle) for the error word read-back: one cudaHostAlloc per process
+unsigned int* pinned_word() {
+    static unsigned int* slab = nullptr;
+    static int next = 0;
+    if (!slab && cudaHostAlloc((void**)&slab, sizeof(unsigned int) * 1024, cudaHostAllocDefault) != cudaSuccess) { slab = nullptr; return nullptr; }
+    unsigned int* w = slab + (next++ % 1024);
+    *w = 0;
+    return w;
+}
+
+
 }  // namespace
 
 // Bump allocator over ONE cudaMalloc.  All small state of a handle lives in a few contiguous 2 MB pages: after
@@ -86,6 +97,14 @@ BigPool g_pool;
 struct Arena {
     unsigned char* base = nullptr;
     size_t cap = 0, used = 0;
+    int device = 0;
+    cudaError_t reserve(size_t bytes, int dev) {
+        device = dev; used = 0;
+        cudaError_t e = g_pool.alloc((void**)&base, bytes, dev);
+        cap = e == cudaSuccess ? bytes : 0;
+        if (e != cudaSuccess) base = nullptr;
+        return e;
+    }
     template <typename T>
     T* take(size_t count) {
         const size_t bytes = ((count ? count : 1) * sizeof(T) + 255) & ~(size_t)255;
@@ -94,7 +113,7 @@ struct Arena {
         used += bytes;
         return p;
     }
-    void release() { if (base) cudaFree(base); base = nullptr; cap = used = 0; }
+    void release() { if (base) g_pool.release(base, cap, device); base = nullptr; cap = used = 0; }
 };
 
 struct prmf_handle {
@@ -170,6 +189,7 @@ struct prmf_handle {
     unsigned long long epi_seq1 = 0, epi_seq2 = 0;
     // deferred objective: per-step history [obj_capacity] of what the objective needs (one cudaMalloc)
     double* hist = nullptr;
+    size_t hist_bytes = 0;
     double *hist_Gu = nullptr, *hist_Gvp = nullptr, *hist_VBp = nullptr, *hist_vh = nullptr;
     bool defer_ok = false;
     double *epi_part2 = nullptr, *epi_vb2 = nullptr;
@@ -670,9 +690,8 @@ int alloc_active_arena(prmf_handle* h, int64_t cap_diag, int64_t cap_off) {
     const size_t n_f64 = (size_t)(h->as_cap_diag + h->as_cap_off);
     const size_t total = ((n_i32 * 4 + 255) & ~(size_t)255) + ((n_f64 * 8 + 255) & ~(size_t)255) +
                          ((sizeof(int64_t) * 2 * (k + 1) + 255) & ~(size_t)255);
-    cudaError_t ea = cudaMalloc((void**)&h->as_arena.base, total);
+    cudaError_t ea = h->as_arena.reserve(total, h->device);
     if (ea != cudaSuccess) return fail(h, PRMF_ERR_NOMEM, "cudaMalloc active set: %s", cudaGetErrorString(ea));
-    h->as_arena.cap = total;
     h->as_f64 = h->as_arena.take<double>(n_f64);
     h->as_i32 = h->as_arena.take<int32_t>(n_i32);
     h->as_off = h->as_arena.take<int64_t>((size_t)2 * (k + 1));
@@ -1476,9 +1495,8 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
         total += pad((size_t)nk + kk2 + 2, d) + pad(1, d) + pad((size_t)h->sm_count * 8, d) + pad(2, d);
         total += pad(1, sizeof(int)) + pad(1, sizeof(unsigned int)) + pad(k, sizeof(int32_t)) + pad(nk, sizeof(int32_t));
         total += pad((size_t)h->obj_capacity * kObjStride, d);
-        cudaError_t ea = cudaMalloc((void**)&h->arena.base, total);
+        cudaError_t ea = h->arena.reserve(total, device);
         if (ea != cudaSuccess) rc = fail(h, PRMF_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", total, cudaGetErrorString(ea));
-        h->arena.cap = total;
     }
 #define ALLOC(ptr, count) if (!rc) rc = dalloc(h, &ptr, (size_t)(count))
 #define TAKE(ptr, T, count) if (!rc) { ptr = h->arena.take<T>((size_t)(count)); if (!ptr) rc = fail(h, PRMF_ERR_NOMEM, "arena exhausted"); }
@@ -1558,7 +1576,8 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
         if (!(ed && atoi(ed) == 0)) {
             const size_t H = (size_t)h->obj_capacity, kk2s = (size_t)kk2;
             const size_t n_gu = H * kk2s, n_gvp = H * h->tpanels * kk2s, n_vbp = H * h->tpanels, n_vh = H * kVhCap;
-            if (dalloc(h, &h->hist, n_gu + n_gvp + n_vbp + n_vh) == PRMF_OK) {
+            h->hist_bytes = sizeof(double) * (n_gu + n_gvp + n_vbp + n_vh);
+            if (g_pool.alloc((void**)&h->hist, h->hist_bytes, device) == cudaSuccess) {
                 h->hist_Gu = h->hist;
                 h->hist_Gvp = h->hist_Gu + n_gu;
                 h->hist_VBp = h->hist_Gvp + n_gvp;
@@ -1579,8 +1598,7 @@ int prmf_create_ex(prmf_handle** out, int device, int64_t m_local, int64_t m_glo
                       sizeof(double) * (256 + 8 * (size_t)k * k + (size_t)kBlkRowsCap * k);
         h->use_block = h->use_epi && h->defer_ok && !(eb && atoi(eb) == 0) && h->blk_smem <= 227 * 1024;
         h->block_forced = eb && atoi(eb) == 1;
-        if (cudaHostAlloc((void**)&h->err_host, sizeof(unsigned int), cudaHostAllocDefault) == cudaSuccess) *h->err_host = 0;
-        else h->err_host = nullptr;
+        h->err_host = pinned_word();
     }
     // opt in to large dynamic shared memory where k needs it
     if (!rc && h->big_k) {
@@ -1619,12 +1637,11 @@ int prmf_destroy(prmf_handle* h) {
         for (int r = 0; r < h->nranks; ++r)
             if (r != h->rank && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
     if (h->ev_sync) cudaEventDestroy(h->ev_sync);
-    if (h->err_host) cudaFreeHost(h->err_host);
     if (h->p2p_buf) cudaFree(h->p2p_buf);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     g_pool.release(h->X, sizeof(double) * (size_t)std::max<int64_t>(1, h->m) * h->ldx, h->device);
     g_pool.release(h->Xt, sizeof(double) * (size_t)h->n * h->ldxt, h->device);
-    if (h->hist) cudaFree(h->hist);
+    g_pool.release(h->hist, h->hist_bytes, h->device);
     g_pool.release(h->X32, sizeof(float) * (size_t)std::max<int64_t>(1, h->m) * h->ldx32, h->device);
     g_pool.release(h->Xt32, sizeof(float) * (size_t)h->n * h->ldxt32, h->device);
     if (h->Vt32) cudaFree(h->Vt32);
@@ -1728,9 +1745,8 @@ int prmf_set_pathways(prmf_handle* h, int32_t P, const int64_t* path_ptr, const 
                              pad(sizeof(int64_t) * (S + 1)) + pad(sizeof(int32_t) * std::max<int64_t>(1, E)) +
                              pad(sizeof(double) * std::max<int64_t>(1, E)) + 3 * pad(sizeof(double) * std::max<int64_t>(1, S)) +
                              pad(sizeof(double) * 3 * (size_t)h->k * P);
-        cudaError_t ea = cudaMalloc((void**)&h->pw_arena.base, total);
+        cudaError_t ea = h->pw_arena.reserve(total, h->device);
         if (ea != cudaSuccess) return fail(h, PRMF_ERR_NOMEM, "cudaMalloc pathways (%zu bytes): %s", total, cudaGetErrorString(ea));
-        h->pw_arena.cap = total;
     }
     int rc = 0;
     auto up = [&](const void* src, size_t bytes, const void** dst) -> int {

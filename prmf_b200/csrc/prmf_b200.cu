@@ -757,7 +757,7 @@ int launch_xv_epi(prmf_handle* h, const double* gv_src = nullptr, int gv_parts =
     int rc = 0;
     KT_SWITCH_RC(h->k, rc, launch_skinny_epi_t, h, 1, h->Xt, h->ldxt, h->n, h->m, h->Vbuf[h->vcur], h->tpanels1,
                  h->tpanel_w1, h->tchunks1, h->trows_per_chunk1, h->tma_smem1, h->Apart, ep);
-    if (rc) return rc;
+    if (rc) { h->failed = true; return rc; }     // the panel counters expect this launch: no further steps on this handle
     LAUNCH_CHECK("skinny_tma_kernel(pass 1 + U update)");
     std::swap(h->U, h->U2);
     return PRMF_OK;
@@ -813,7 +813,7 @@ int launch_xtu_epi(prmf_handle* h, int mode, double* packed_dst, int hist_slot =
     int rc = 0;
     KT_SWITCH_RC(h->k, rc, launch_skinny_epi_t, h, mode, h->X, h->ldx, h->m, h->n, h->U, h->tpanels, h->tpanel_w,
                  h->tchunks, h->trows_per_chunk, h->tma_smem2, h->Bpart, ep);
-    if (rc) return rc;
+    if (rc) { h->failed = true; return rc; }
     LAUNCH_CHECK(mode == 3 ? "skinny_tma_kernel(pass 2 + pack)" : mode == 4 ? "skinny_tma_kernel(pass 2 + exchange + V update)"
                                                                             : "skinny_tma_kernel(pass 2 + V update)");
     if (mode != 3) h->vcur ^= 1;

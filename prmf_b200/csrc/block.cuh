@@ -25,31 +25,45 @@
 
 namespace prmf {
 
-// Low-latency exchange entries: a value travels with its sequence number in ONE 16-byte store, so the receiver needs
-// neither a fence nor a separate flag -- it polls the entry itself until the sequence number is the expected one
-// (one one-way NVLink hop; the pattern of NCCL's LL protocol, here with 8-byte payloads).
+// Low-latency exchange entries (NCCL's LL protocol with 64-bit payloads): a double travels as TWO 8-byte words, each
+// carrying 32 bits of the value and the low 32 bits of the step's sequence number,
+//     word0 = seq32 << 32 | lo32(value)        word1 = seq32 << 32 | hi32(value)
+// written by one 16-byte store.  The receiver needs neither a fence nor a separate flag: it polls the entry itself until
+// BOTH words carry the expected sequence number.  Only 8-byte single-copy atomicity is assumed (the PTX memory model
+// treats a .v2 access as two scalar accesses): if the halves of the 16-byte store ever became visible separately, each
+// half still validates itself.  One one-way NVLink hop per exchange.
 __device__ __forceinline__ void ll_store(ulonglong2* dst, double v, unsigned long long seq) {
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(__double_as_longlong(v)), "l"(seq) : "memory");
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long tag = (seq & 0xffffffffull) << 32;
+    const unsigned long long w0 = tag | (bits & 0xffffffffull), w1 = tag | (bits >> 32);
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ bool ll_valid(unsigned long long w0, unsigned long long w1, unsigned long long seq) {
+    const unsigned long long tag = seq & 0xffffffffull;
+    return (w0 >> 32) == tag && (w1 >> 32) == tag;
+}
+__device__ __forceinline__ double ll_value(unsigned long long w0, unsigned long long w1) {
+    return __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
 }
 
 __device__ __forceinline__ double ll_wait(const ulonglong2* src, unsigned long long seq, unsigned int* err,
                                           unsigned long long timeout_ns) {
-    unsigned long long t0 = 0, lo, hi;
+    unsigned long long t0 = 0, w0, w1;
     unsigned int polls = 0;
     for (;;) {
-        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(src) : "memory");
-        if (hi == seq) break;
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+        if (ll_valid(w0, w1, seq)) break;
         __nanosleep(20);
         if ((++polls & 255u) == 0u) {
             const unsigned long long now = blk_gtime();
             if (t0 == 0) t0 = now;
             if (now - t0 > timeout_ns || ld_volatile_u32(err) != 0u) {
                 atomicOr(err, kErrTimeoutPeer);
-                break;
+                return 0.0;
             }
         }
     }
-    return __longlong_as_double((long long)lo);
+    return ll_value(w0, w1);
 }
 
 // Sum over ranks of one entry: the entries of ALL ranks are polled together (one round of local loads per sweep
@@ -65,17 +79,16 @@ __device__ __forceinline__ double ll_gather(const ulonglong2* mine, size_t xpar,
 #pragma unroll
     for (int r = 0; r < kMaxPeers; ++r) v[r] = 0.0;
     while (pend) {
-        unsigned long long lo[kMaxPeers], hi[kMaxPeers];
+        unsigned long long w0[kMaxPeers], w1[kMaxPeers];
 #pragma unroll
         for (int r = 0; r < kMaxPeers; ++r) {
-            hi[r] = ~0ull;
-            lo[r] = 0ull;
+            w0[r] = w1[r] = 0ull;
             if ((pend >> r) & 1u)
-                asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo[r]), "=l"(hi[r]) : "l"(mine + (xpar + r) * xcount + idx));
+                asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[r]), "=l"(w1[r]) : "l"(mine + (xpar + r) * xcount + idx));
         }
 #pragma unroll
         for (int r = 0; r < kMaxPeers; ++r)
-            if (hi[r] == seq) { v[r] = __longlong_as_double((long long)lo[r]); pend &= ~(1u << r); }
+            if (((pend >> r) & 1u) && ll_valid(w0[r], w1[r], seq)) { v[r] = ll_value(w0[r], w1[r]); pend &= ~(1u << r); }
         if (pend) {
             __nanosleep(20);
             if ((++polls & 255u) == 0u) {

@@ -61,7 +61,7 @@ struct BlockParams {
     unsigned long long timeout_ns;
     // exchange over ranks (nranks <= 1: none)
     int nranks, rank;
-    ulonglong2* xbuf[kMaxPeers];     // rank r's receive buffer: [parity 2][src rank kMaxPeers][xcount] of {value bits, sequence}
+    ulonglong2* xbuf[kMaxPeers];     // rank r's receive buffer: [parity 2][src rank kMaxPeers][xcount] LL entries (block.cuh)
     size_t xcount;                   // entries per (parity, src) slot: n*K + K*K, padded
     unsigned long long xbase;        // exchanges (= pass-2 executions of this kernel) before this launch
 };

@@ -151,19 +151,23 @@ int prmf_nccl_load(const char* libnccl_path);
 int prmf_comm_unique_id(uint8_t* id_out /* PRMF_UNIQUE_ID_BYTES */);
 int prmf_comm_init(prmf_handle* h, int rank, int nranks, const uint8_t* id);
 
-/* Optional: fuse the per-step all-reduce into the V-update kernel over NVLink peer memory (one-shot sum of
- * all ranks' packed buffers with plain P2P loads, flag barrier in peer memory) instead of calling NCCL.
- * Every rank exports a CUDA IPC handle of its exchange buffer (PRMF_IPC_HANDLE_BYTES), the handles are
- * gathered by the host (any transport) and every rank attaches all of them.  Needs one process per GPU on
- * one node with peer access; prmf_comm_init is still required (set-up reductions use NCCL). */
+/* The per-step sum over ranks through NVLink / CUDA-IPC peer memory instead of NCCL.  Every rank exports a CUDA IPC
+ * handle of its exchange buffer (PRMF_IPC_HANDLE_BYTES), the handles are gathered by the host (any transport) and every
+ * rank attaches all of them; then all ranks call the collective prmf_p2p_finalize, which agrees on the variant:
+ *   - k <= 10, every rank able to run the persistent step kernel with the same split of the genes (the default):
+ *     the sum is part of the pass-2 tail of that kernel -- every thread block pushes the local sums of its share of
+ *     genes into every rank's receive slots as self-validating {32 value bits | 32 sequence bits} word pairs (one
+ *     16-byte store each, no fence, no flag), polls the same entries of all ranks in its own memory, adds them in rank
+ *     order and updates its rows of V.  No collective launch; bitwise identical on all ranks.
+ *   - otherwise: the packed buffers of all ranks are pulled with P2P loads inside the V-update kernel (flag barrier in
+ *     peer memory), or inside the pass-2 kernel with PRMF_XCHG=1.
+ * Needs one process per rank on one node with peer access (or several ranks sharing one device: IPC works there too).
+ * prmf_comm_init is OPTIONAL for the first variant: without a communicator the set-up reductions (||X||^2, the
+ * agreement itself) are summed over the same peer buffers; configurations that need the other variants then fail with
+ * PRMF_ERR_STATE.  All device-side waits on peers are bounded (PRMF_ERR_TIMEOUT). */
 #define PRMF_IPC_HANDLE_BYTES 64
 int prmf_p2p_export(prmf_handle* h, uint8_t* handle_out);
 int prmf_p2p_attach(prmf_handle* h, int rank, int nranks, const uint8_t* handles /* nranks x 64 bytes */);
-/* Collective over the ranks, after prmf_p2p_attach succeeded on ALL of them: agree on the exchange path.  When every
- * rank runs the fused-tail X-stream kernels (k <= 10), the exchange moves INTO the pass-2 kernel: every CTA
- * publishes the X^T U sums of its share of genes, flags them in every peer's memory, waits for the peers' same
- * share and adds the ranks' buffers in rank order over P2P loads, then updates its rows of V -- no collective
- * launch and no separate V-update launch.  Otherwise the exchange stays in the V-update kernel. */
 int prmf_p2p_finalize(prmf_handle* h);
 
 /* How the per-step sum over ranks is done: 0 one rank, 1 ncclAllReduce, 2 NVLink peer loads inside the V-update

@@ -281,9 +281,11 @@ def nccl_load():
 
 
 def attach_collectives(eng, ctx, p2p=None):
-    """Give the engine of a multi-rank run its communicators: NCCL (set-up reductions, and the per-step
-    all-reduce when peer access is unavailable) and -- unless PRMF_P2P=0 -- the NVLink peer exchange that fuses
-    the per-step all-reduce into the V-update kernel.  Collective over `ctx`: call on every rank."""
+    """Give the engine of a multi-rank run its communicators: NCCL (set-up reductions, and the per-step all-reduce of
+    configurations that cannot use peer memory) and -- unless PRMF_P2P=0 -- the NVLink / CUDA-IPC peer buffers through
+    which the per-step sum over ranks runs inside the kernels (pushed inside the persistent step kernel for k <= 10,
+    pulled inside the V update otherwise).  Ranks that share one device, or PRMF_NCCL=0, skip NCCL altogether.
+    Collective over `ctx`: call on every rank."""
     import os
     if ctx.world <= 1:
         return eng

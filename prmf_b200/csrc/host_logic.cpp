@@ -27,7 +27,8 @@ extern "C" int64_t prmf_host_restrict(const double* mass_row, const double* quad
     const int64_t lo = (int64_t)std::floor(vi);
     const int64_t hi = std::min<int64_t>(lo + 1, n - 1);
     const double g = vi - (double)lo;
-    std::vector<double> tmp(scores_out, scores_out + n);
+    static thread_local std::vector<double> tmp;                      // scratch kept across calls (one per host thread)
+    tmp.assign(scores_out, scores_out + n);
     std::nth_element(tmp.begin(), tmp.begin() + lo, tmp.end());
     const double a = tmp[lo];
     double b = a;
